@@ -1,0 +1,212 @@
+/*
+ * polyphemus_b200.h — C ABI of libpolyphemus_b200.so (hand-written sm_100a CUDA).
+ *
+ * Drop-in boundary for ONE hot path of EmanueleCosenza/polyphemus: batched pianoroll-structure -> graph
+ * construction (reference data.py:14-204) and the relational graph-convolution stack of its graph VAE
+ * (reference model.py:30-135 GCL, model.py:167-208 GCN), forward and backward.
+ *
+ * The reference is pure Python and has no FFI; each entry point below names the reference lines it
+ * replaces. INTEGRATION.md shows the ctypes stub a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter is documented as host;
+ *   - the caller owns all memory; the library never allocates device memory (workspace sizes come from the
+ *     *_workspace_bytes queries) and never synchronises the stream;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and returns 0 on success or a
+ *     negative pb_status; pb_last_error() returns a thread-local message for the last failure;
+ *   - row-major everywhere; `ld*` are leading dimensions in ELEMENTS;
+ *   - integer outputs are bit-exact with the reference; floating-point outputs follow DESIGN.md tolerances;
+ *   - there is NO CPU fallback: calls fail with PB_ERR_CUDA when no sm_100 device/context is usable.
+ */
+#ifndef POLYPHEMUS_B200_H
+#define POLYPHEMUS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB_VERSION 100  /* 0.1.0 */
+
+typedef void* pb_stream_t; /* cudaStream_t */
+
+enum pb_status {
+  PB_OK = 0,
+  PB_ERR_INVALID = -1,   /* bad argument (shape, alignment, null pointer) */
+  PB_ERR_CUDA = -2,      /* CUDA runtime / driver error, message in pb_last_error() */
+  PB_ERR_WORKSPACE = -3, /* workspace too small */
+  PB_ERR_UNSUPPORTED = -4
+};
+
+/* Arithmetic mode of the tensor-core contractions (DESIGN.md "Precision modes").
+ *   PB_F32  : operands split into TF32 hi+lo, three tcgen05 kind::tf32 MMAs per k-step, fp32 accumulate
+ *             (fp32-grade: the parity mode, rtol 1e-4 / atol 1e-5 against the fp32 reference);
+ *   PB_BF16 : operands rounded to bf16, one tcgen05 kind::f16 MMA per k-step, fp32 accumulate. */
+enum pb_dtype { PB_F32 = 0, PB_BF16 = 1 };
+
+enum { PB_N_TRACKS = 4, PB_N_TIMESTEPS = 32, PB_N_DISTS = 32, PB_N_RELATIONS = 6 };
+
+int pb_version(void);
+const char* pb_last_error(void);
+/* Host-side query: SM count and compute capability of the current device. */
+int pb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph construction  —  replaces data.py:141-204 graph_from_tensor (+ get_*_edges data.py:14-138) and
+ * the per-sequence loop + Batch.from_data_list of model.py:596-607 / train.py:152-156.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Pass 1. s_tensor: uint8/bool [n_bars, 4, 32] (all bars of all sequences, sequence-major). Empty bars get
+ * the fake activation s[bar,0,0]=1 IN PLACE (data.py:152-153). Outputs:
+ *   bar_bits  u32 [n_bars,4]   bit t of word k = activation (track k, timestep t)
+ *   node_ptr  i32 [n_bars+1]   exclusive scan of nodes per bar
+ *   edge_ptr  i32 [n_bars+1]   exclusive scan of edges per bar (fake self-edge counted, data.py:173-176)
+ *   totals    i64 [4]          {N, E, n_drum_nodes, max_nodes_per_bar}                                  */
+size_t pb_graph_workspace_bytes(int64_t n_bars);
+int pb_graph_count(uint8_t* s_tensor, int64_t n_bars, uint32_t* bar_bits, int32_t* node_ptr,
+                   int32_t* edge_ptr, int64_t* totals, void* workspace, size_t workspace_bytes,
+                   pb_stream_t stream);
+
+/* Pass 2. Emits the reference's arrays in the reference's order (bit-exact):
+ *   edge_index    i64 [2,E]  global node ids (PyG collate increment)      data.py:173,193 / model.py:604
+ *   edge_type     u8  [E]    0..3 track, 4 onset, 5 next                  constants.py:52-58
+ *   edge_dist     u8  [E]    timestep distance 0..31                      data.py:45,74,116
+ *   edge_attrs    f32 [E,33] optional (NULL to skip): col0=type, col 1+dist=1   data.py:179-182
+ *   node_features f32 [N,4]  one-hot track                                data.py:124-138
+ *   is_drum       u8  [N]                                                 data.py:185
+ *   bars          i64 [N]    bar index inside its sequence                data.py:202
+ *   batch         i64 [N]    sequence index                               PyG add_batch
+ *   node_track    u8  [N]    track of the node (internal helper, optional NULL)                          */
+int pb_graph_fill(const uint32_t* bar_bits, const int32_t* node_ptr, const int32_t* edge_ptr,
+                  int64_t n_bars, int32_t bars_per_seq, int64_t* edge_index, int64_t n_edges,
+                  uint8_t* edge_type, uint8_t* edge_dist, float* edge_attrs, float* node_features,
+                  uint8_t* is_drum, int64_t* bars, int64_t* batch, uint8_t* node_track,
+                  pb_stream_t stream);
+
+/* edge_attrs f32 [E,33] from (type, dist)  — data.py:179-182, materialised lazily. */
+int pb_edge_attrs_encode(const uint8_t* edge_type, const uint8_t* edge_dist, int64_t n_edges,
+                         float* edge_attrs, pb_stream_t stream);
+/* Inverse, for foreign graphs handed to GCN/GCL: edge_type f32 [E] (stride in elements) and one-hot
+ * edge_attr f32 [E,32] (row stride in elements)  ->  u8 type, u8 dist (argmax).  model.py:193-194     */
+int pb_edge_attrs_decode(const float* edge_type, int64_t type_stride, const float* edge_attr,
+                         int64_t attr_stride, int64_t n_edges, uint8_t* type_out, uint8_t* dist_out,
+                         pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CSR plan — replaces the per-relation boolean compaction masked_edge_index/attrs (model.py:30-38,
+ * 104-105) and PyG's gather/scatter bookkeeping. Destination-sorted segments keyed by (dst, relation)
+ * for the forward mean-aggregation; source-sorted records for the backward scatter. Deterministic:
+ * edges inside a segment are ordered by their index in edge_index.
+ *   in_ptr  i32 [N*R+1]   in_edge i32 [E] = src | dist<<26     in_eid i32 [E] original edge id
+ *   out_ptr i32 [N+1]     out_rec int4 [E] = {dst, rel | dist<<8, eid, |segment(dst,rel)|}
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct pb_csr {
+  int64_t n_nodes;
+  int64_t n_edges;
+  int32_t n_relations;
+  int32_t reserved;
+  const int32_t* in_ptr;
+  const int32_t* in_edge;
+  const int32_t* in_eid;
+  const int32_t* out_ptr;
+  const void* out_rec;
+} pb_csr_t;
+
+size_t pb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t n_relations);
+int pb_csr_build(const int64_t* edge_index, const uint8_t* edge_type, const uint8_t* edge_dist,
+                 int64_t n_nodes, int64_t n_edges, int32_t n_relations, int32_t* in_ptr, int32_t* in_edge,
+                 int32_t* in_eid, int32_t* out_ptr, void* out_rec, void* workspace, size_t workspace_bytes,
+                 pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Edge network table — replaces nn.Linear(32,d) applied to one-hot distances (model.py:127-129, 175):
+ * T[k,:] = nn_weight[:,k] + nn_bias.   Backward (fixed-order reduction of the per-CTA partials of pb_agg_bwd):
+ * g_nn_weight[c,k] = dT[k,c], g_nn_bias[c] = sum_k dT[k,c].
+ * ---------------------------------------------------------------------------------------------- */
+int pb_edge_table_fwd(const float* nn_weight, const float* nn_bias, int32_t d, float* table,
+                      pb_stream_t stream);
+int pb_edge_table_bwd(const float* dtable_partials, int32_t n_partials, int32_t d, float* g_nn_weight,
+                      float* g_nn_bias, pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Message + mean aggregation — replaces GCL.message (model.py:123-135) and propagate/scatter-mean per
+ * relation (model.py:103-111):  H[v,r,:] = mean_{e in seg(v,r)} keep_e * relu(x[src_e] * T[dist_e]).
+ * Writes the GEMM operand  A[v, :] = [H[v,0] | ... | H[v,R-1] | x[v]]  (row stride lda):
+ *   PB_BF16: A bf16;   PB_F32: A_hi / A_lo fp32 (TF32 split, A_lo may not be NULL).
+ * Dropout (model.py:133, p hard-wired 0.1 in training): keep mask from Philox4x32-10 keyed by `seed`,
+ * counter (edge id, channel/4); pb_dropout_mask exposes the same mask for checking.
+ * Backward: gx[u] = gy_res[u] + dA[u, R*d:] + sum_{e: src=u} dH[dst_e, rel_e]/cnt * keep * 1[x*T>0] * T[dist_e]
+ *           dT partials per CTA (deterministic, reduced by pb_edge_table_bwd).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, void* a_hi, void* a_lo,
+               int64_t lda, int32_t dtype, float p_drop, uint64_t seed, pb_stream_t stream);
+int32_t pb_agg_bwd_num_partials(void);
+int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
+               int64_t ldda, int32_t dtype, const float* gy_res, float* gx, float* dtable_partials,
+               float p_drop, uint64_t seed, pb_stream_t stream);
+int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep /*[E,d]*/,
+                    pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-relation weight transform — replaces the 7 matmuls of GCL.forward (model.py:112,116,119):
+ *   out = A @ Wcat + bias,  Wcat = [weight[0]; ...; weight[R-1]; root]  ((R+1)d x d).
+ * tcgen05 (TMEM accumulators, TMA operand loads). Weight operands are prepared once per call by
+ * pb_weight_prep (transposed copy for the forward, dtype conversion / TF32 split).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_weight_prep(const float* weight, const float* root, int32_t n_relations, int32_t d, int32_t dtype,
+                   void* wcat_hi, void* wcat_lo, void* wcat_t_hi, void* wcat_t_lo, pb_stream_t stream);
+/* out f32 [M, d] = A[M,K] @ Wcat[K,d] + bias (bias may be NULL).  wcat_t_* is [d, K] (K contiguous). */
+int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                     const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
+                     int32_t k, int32_t dtype, pb_stream_t stream);
+/* dA [M,K] = g[M,d] @ Wcat^T.  g_* is the GEMM-operand copy of the output gradient (bf16, or f32 hi/lo);
+ * dA is bf16 (PB_BF16) or f32 (PB_F32). */
+int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
+                          const void* wcat_lo, void* d_a, int64_t ldda, int64_t m, int32_t d, int32_t k,
+                          int32_t dtype, pb_stream_t stream);
+/* dWcat f32 [K,d] = A^T @ g (fixed-order split-K over the node dimension, deterministic). */
+size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k);
+int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
+                            const void* g_lo, int64_t ldg, float* d_wcat, int64_t m, int32_t d, int32_t k,
+                            int32_t dtype, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+/* Plain-fp32 CUDA-core contraction D[M,N] = A[M,K] @ B[K,N] (+bias) used by the tests to cross-check the
+ * tensor-core kernels on device; not on the product path. */
+int pb_gemm_f32_check(const float* a, int64_t lda, const float* b, int64_t ldb, const float* bias, float* d_out,
+                      int64_t ldd, int64_t m, int32_t n, int32_t k, int32_t trans_a, int32_t trans_b,
+                      pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm(batch statistics over all node rows) + ReLU + residual — replaces GCN.forward lines
+ * model.py:198-206:  y = x + relu(gamma * (out - mean) * rstd + beta).
+ * stats: mean/var over the m rows (biased var for normalisation, unbiased for running_var, eps 1e-5,
+ * momentum 0.1 — torch.nn.BatchNorm1d). In eval mode pass running stats through pb_bn_prepare_eval.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pb_bn_workspace_bytes(int64_t m, int32_t d);
+/* bn_coef f32 [3,d] = {mean, scale = gamma*rstd, beta}; save_mean_rstd f32 [2,d];
+ * running_mean/var updated in place when not NULL. */
+int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const float* gamma, const float* beta,
+                float eps, float momentum, float* running_mean, float* running_var, float* save_mean_rstd,
+                float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+int pb_bn_prepare_eval(const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, int32_t d, float* bn_coef,
+                       pb_stream_t stream);
+/* y = x_res + relu((out-mean)*scale + beta)   (x_res may be NULL: y = relu(...)); apply_relu=0 skips the ReLU */
+int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef,
+                       float* y, int64_t m, int32_t d, int32_t apply_relu, pb_stream_t stream);
+/* Backward of y = x + relu(bn(out)) wrt out (training statistics):
+ *   g_out f32 [m,d] (+ GEMM-operand copies g_hi/g_lo in `dtype`), g_gamma, g_beta, g_bias(=colsum g_out).
+ *   The residual branch gradient is gy itself (consumed by pb_agg_bwd as gy_res). */
+int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
+                       const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
+                       int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma, float* g_beta,
+                       float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+/* Operand conversion for a plain GCL (no BN): g f32 [m,d] -> g_hi/g_lo in `dtype`, and g_bias = colsum. */
+int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d, int32_t dtype, void* g_hi, void* g_lo,
+                 int64_t ldg, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLYPHEMUS_B200_H */

@@ -1,0 +1,113 @@
+"""ctypes binding of libpolyphemus_b200.so (C ABI declared in include/polyphemus_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or a call fails, an exception is raised.
+Build with ``python -m polyphemus_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libpolyphemus_b200.so")
+
+PB_F32 = 0
+PB_BF16 = 1
+N_RELATIONS = 6
+N_DISTS = 32
+
+
+class PolyphemusB200Error(RuntimeError):
+    pass
+
+
+class CsrStruct(Structure):
+    _fields_ = [
+        ("n_nodes", c_int64), ("n_edges", c_int64), ("n_relations", c_int32), ("reserved", c_int32),
+        ("in_ptr", c_void_p), ("in_edge", c_void_p), ("in_eid", c_void_p), ("out_ptr", c_void_p),
+        ("out_rec", c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/polyphemus_b200.h (tests check this)
+_P = c_void_p
+SIGNATURES = {
+    "pb_version": (c_int, []),
+    "pb_last_error": (c_char_p, []),
+    "pb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "pb_graph_workspace_bytes": (c_size_t, [c_int64]),
+    "pb_graph_count": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pb_graph_fill": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pb_edge_attrs_encode": (c_int, [_P, _P, c_int64, _P, _P]),
+    "pb_edge_attrs_decode": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
+    "pb_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "pb_csr_build": (c_int, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pb_edge_table_fwd": (c_int, [_P, _P, c_int32, _P, _P]),
+    "pb_edge_table_bwd": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
+    "pb_agg_fwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, _P, c_int64, c_int32, c_float, c_uint64, _P]),
+    "pb_agg_bwd_num_partials": (c_int32, []),
+    "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, c_float,
+                           c_uint64, _P]),
+    "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
+    "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
+    "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "pb_rgcn_gemm_bwd_weight_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "pb_rgcn_gemm_bwd_weight": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32,
+                                        _P, c_size_t, _P]),
+    "pb_gemm_f32_check": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32,
+                                  c_int32, _P]),
+    "pb_bn_workspace_bytes": (c_size_t, [c_int64, c_int32]),
+    "pb_bn_stats": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pb_bn_prepare_eval": (c_int, [_P, _P, _P, _P, c_float, c_int32, _P, _P]),
+    "pb_bn_relu_res_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "pb_bn_relu_res_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P,
+                                   _P, _P, c_size_t, _P]),
+    "pb_grad_prep": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PolyphemusB200Error(
+                f"{LIB_PATH} not found: build the CUDA library first (python -m polyphemus_b200.build). "
+                "polyphemus_b200 has no CPU or PyTorch fallback.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().pb_last_error()
+        raise PolyphemusB200Error(f"{what} failed with status {rc}: {msg.decode() if msg else '?'}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise PolyphemusB200Error(
+                "polyphemus_b200 kernels only run on CUDA tensors (sm_100a); there is no CPU fallback")

@@ -1,0 +1,345 @@
+// BatchNorm (batch statistics over all node rows) + ReLU + residual, forward and backward.
+//
+// Replaces GCN.forward's per-layer tail (reference model.py:198-206): PyG BatchNorm == nn.BatchNorm1d(d,
+// eps=1e-5, momentum=0.1) over the N node rows, F.relu, `residual + x`; and what autograd derives for them.
+// All kernels are HBM-bound streaming passes with 16-byte accesses. Column reductions are two-stage with a
+// fixed CTA->row-range partition and a fixed combination order (double precision in the tiny second stage),
+// so results are bit-reproducible; the variance uses sums shifted by the first row to avoid cancellation.
+//
+// bn_coef layout (f32 [3,d]): row 0 = mean, row 1 = scale (= gamma * rstd), row 2 = beta
+//   y = x_res + relu((out - mean) * scale + beta)
+#include "common.cuh"
+
+namespace pb {
+
+constexpr int kColThreads = 256;
+constexpr int kColMaxCtas = 148 * 4;
+
+static inline int col_ctas(int64_t m) {
+  int64_t n = (m + 127) / 128;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(n, kColMaxCtas));
+}
+
+// Each CTA reduces a contiguous row range for every column; thread = (row group, float4 column chunk).
+// partials: [gridDim.x][NV][d]
+template <int NV, class Load>
+__device__ __forceinline__ void column_partials(int64_t m, int d, float* __restrict__ partials, Load load) {
+  extern __shared__ float red[];  // [NV][nrg][d]
+  const int nchunk = d >> 2;
+  const int nrg = kColThreads / nchunk;
+  const int rg = threadIdx.x / nchunk, c = threadIdx.x - rg * nchunk;
+  const int64_t per = (m + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = r0 + per < m ? r0 + per : m;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < nrg) {
+    for (int64_t r = r0 + rg; r < r1; r += nrg) {
+      float4 v[NV];
+      load(r, c, v);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(red + ((size_t)i * nrg + rg) * d)[c] = acc[i];
+  }
+  __syncthreads();
+  if (rg == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int g = 0; g < nrg; ++g) {
+        const float4 v = reinterpret_cast<const float4*>(red + ((size_t)i * nrg + g) * d)[c];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      reinterpret_cast<float4*>(partials + ((size_t)blockIdx.x * NV + i) * d)[c] = s;
+    }
+  }
+}
+
+static inline size_t col_smem(int nv, int d) { return (size_t)nv * (kColThreads / (d / 4)) * d * sizeof(float); }
+
+// ------------------------------------------------------------------------------------------------ forward stats
+__global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const float* __restrict__ out, int64_t ldo,
+                                                                      int64_t m, int d, float* __restrict__ partials) {
+  column_partials<2>(m, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 x = ld_stream4(out + (size_t)r * ldo + 4 * c);
+    const float4 k = ldg4(out + 4 * c);  // shift = first row (exactly representable, cancels in the variance)
+    const float4 dlt = make_float4(x.x - k.x, x.y - k.y, x.z - k.z, x.w - k.w);
+    v[0] = dlt;
+    v[1] = make_float4(dlt.x * dlt.x, dlt.y * dlt.y, dlt.z * dlt.z, dlt.w * dlt.w);
+  });
+}
+
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int n_part, const float* __restrict__ out,
+                                         int64_t m, int d, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float momentum,
+                                         float* __restrict__ running_mean, float* __restrict__ running_var,
+                                         float* __restrict__ save_mean_rstd, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int p = 0; p < n_part; ++p) {
+    s1 += (double)partials[((size_t)p * 2 + 0) * d + c];
+    s2 += (double)partials[((size_t)p * 2 + 1) * d + c];
+  }
+  const double n = (double)m;
+  const double mean = (double)out[c] + s1 / n;
+  double var = (s2 - s1 * s1 / n) / n;
+  if (var < 0.0) var = 0.0;
+  const float meanf = (float)mean, varf = (float)var;
+  const float rstd = (float)(1.0 / sqrt((double)varf + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * meanf;
+  if (running_var) {
+    const float unbiased = m > 1 ? (float)(var * n / (n - 1.0)) : varf;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+  save_mean_rstd[c] = meanf;
+  save_mean_rstd[d + c] = rstd;
+  coef[c] = meanf;
+  coef[d + c] = gamma[c] * rstd;
+  coef[2 * d + c] = beta[c];
+}
+
+__global__ void bn_prepare_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps, int d,
+                                       float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  coef[c] = rm[c];
+  coef[d + c] = gamma[c] * (float)(1.0 / sqrt((double)rv[c] + (double)eps));
+  coef[2 * d + c] = beta[c];
+}
+
+// ------------------------------------------------------------------------------------------------ forward apply
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ out, int64_t ldo,
+                                                      const float* __restrict__ x_res, const float* __restrict__ coef,
+                                                      float* __restrict__ y, int64_t m, int d) {
+  const int nchunk = d >> 2;
+  const int64_t total = m * nchunk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / nchunk;
+    const int c = (int)(i - r * nchunk);
+    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+    const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
+    float4 z = make_float4((o.x - mu.x) * sc.x + be.x, (o.y - mu.y) * sc.y + be.y, (o.z - mu.z) * sc.z + be.z,
+                           (o.w - mu.w) * sc.w + be.w);
+    if (RELU) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
+    if (RES) {
+      const float4 xr = ld_stream4(x_res + (size_t)r * d + 4 * c);
+      z.x += xr.x; z.y += xr.y; z.z += xr.z; z.w += xr.w;
+    }
+    st_stream4(y + (size_t)r * d + 4 * c, z);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+// pass 1: g_beta = sum gz, g_gamma = sum gz * xhat   with gz = gy * 1[(out-mean)*scale+beta > 0]
+__global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const float* __restrict__ gy,
+                                                                    const float* __restrict__ out, int64_t ldo,
+                                                                    const float* __restrict__ coef,
+                                                                    const float* __restrict__ mean_rstd, int64_t m,
+                                                                    int d, float* __restrict__ partials) {
+  column_partials<2>(m, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
+    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+    const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
+    const float4 rs = ldg4(mean_rstd + d + 4 * c);
+    const float4 ctr = make_float4(o.x - mu.x, o.y - mu.y, o.z - mu.z, o.w - mu.w);
+    float4 gz;
+    gz.x = ctr.x * sc.x + be.x > 0.f ? g.x : 0.f;
+    gz.y = ctr.y * sc.y + be.y > 0.f ? g.y : 0.f;
+    gz.z = ctr.z * sc.z + be.z > 0.f ? g.z : 0.f;
+    gz.w = ctr.w * sc.w + be.w > 0.f ? g.w : 0.f;
+    v[0] = gz;
+    v[1] = make_float4(gz.x * ctr.x * rs.x, gz.y * ctr.y * rs.y, gz.z * ctr.z * rs.z, gz.w * ctr.w * rs.w);
+  });
+}
+
+// sums [n_part][NV][d] -> out_v[NV][d] in double, fixed order
+template <int NV>
+__global__ void col_finalize_kernel(const float* __restrict__ partials, int n_part, int d, float* __restrict__ o0,
+                                    float* __restrict__ o1) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  double s[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s[i] = 0.0;
+  for (int p = 0; p < n_part; ++p)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s[i] += (double)partials[((size_t)p * NV + i) * d + c];
+  if (o0) o0[c] = (float)s[0];
+  if (NV > 1 && o1) o1[c] = (float)s[NV > 1 ? 1 : 0];
+}
+
+template <bool BF16>
+__device__ __forceinline__ void store_g(void* g_hi, void* g_lo, size_t off, float4 v) {
+  if constexpr (BF16) {
+    st_stream2(reinterpret_cast<__nv_bfloat16*>(g_hi) + off, make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)));
+  } else {
+    const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    st_stream4(reinterpret_cast<float*>(g_hi) + off, h);
+    st_stream4(reinterpret_cast<float*>(g_lo) + off, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+  }
+}
+
+// pass 2: g_out = scale * (gz - g_beta/m - xhat * g_gamma/m), written as the GEMM operand; column sums of
+// g_out (the bias gradient of the layer feeding this BatchNorm) leave as partials.
+template <bool BF16>
+__global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(
+    const float* __restrict__ gy, const float* __restrict__ out, int64_t ldo, const float* __restrict__ coef,
+    const float* __restrict__ mean_rstd, const float* __restrict__ g_gamma, const float* __restrict__ g_beta,
+    int64_t m, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg, float* __restrict__ partials) {
+  const float inv_m = 1.f / (float)m;
+  column_partials<1>(m, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
+    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+    const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
+    const float4 rs = ldg4(mean_rstd + d + 4 * c);
+    const float4 gg = ldg4(g_gamma + 4 * c), gb = ldg4(g_beta + 4 * c);
+    float4 res;
+#define PB_BN_BWD(f)                                                   \
+  {                                                                    \
+    const float ctr = o.f - mu.f;                                      \
+    const float gz = ctr * sc.f + be.f > 0.f ? g.f : 0.f;              \
+    const float xhat = ctr * rs.f;                                     \
+    res.f = sc.f * (gz - gb.f * inv_m - xhat * (gg.f * inv_m));        \
+  }
+    PB_BN_BWD(x) PB_BN_BWD(y) PB_BN_BWD(z) PB_BN_BWD(w)
+#undef PB_BN_BWD
+    store_g<BF16>(g_hi, g_lo, (size_t)r * ldg + 4 * c, res);
+    v[0] = res;
+  });
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kColThreads) grad_prep_kernel(const float* __restrict__ g, int64_t ldg_in, int64_t m,
+                                                               int d, void* __restrict__ g_hi, void* __restrict__ g_lo,
+                                                               int64_t ldg, float* __restrict__ partials) {
+  column_partials<1>(m, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 x = ld_stream4(g + (size_t)r * ldg_in + 4 * c);
+    store_g<BF16>(g_hi, g_lo, (size_t)r * ldg + 4 * c, x);
+    v[0] = x;
+  });
+}
+
+static int check_md(int64_t m, int d, const char* who) {
+  PB_REQUIRE(m > 0, "%s: m must be positive", who);
+  PB_REQUIRE(d >= 64 && d % 64 == 0 && d <= 1024, "%s: d=%d must be a multiple of 64 in [64, 1024]", who, d);
+  return PB_OK;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" size_t pb_bn_workspace_bytes(int64_t m, int32_t d) {
+  if (m <= 0 || d <= 0) return 0;
+  return align_up((size_t)col_ctas(m) * 2 * d * sizeof(float), 256);
+}
+
+extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, float* save_mean_rstd,
+                           float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+  int rc = check_md(m, d, "pb_bn_stats");
+  if (rc) return rc;
+  PB_REQUIRE(out && gamma && beta && save_mean_rstd && bn_coef && workspace, "pb_bn_stats: null pointer");
+  PB_REQUIRE(ldo >= d && ldo % 4 == 0, "pb_bn_stats: bad ldo");
+  PB_REQUIRE(workspace_bytes >= pb_bn_workspace_bytes(m, d), "pb_bn_stats: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int ctas = col_ctas(m);
+  float* partials = reinterpret_cast<float*>(workspace);
+  bn_stats_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, m, d, partials);
+  PB_LAUNCH_CHECK();
+  bn_stats_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, out, m, d, gamma, beta, eps, momentum,
+                                                           running_mean, running_var, save_mean_rstd, bn_coef);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_bn_prepare_eval(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, int32_t d, float* bn_coef, pb_stream_t stream) {
+  PB_REQUIRE(gamma && beta && running_mean && running_var && bn_coef && d > 0, "pb_bn_prepare_eval: bad arguments");
+  bn_prepare_eval_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, eps, d,
+                                                                        bn_coef);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef, float* y,
+                                  int64_t m, int32_t d, int32_t apply_relu, pb_stream_t stream) {
+  int rc = check_md(m, d, "pb_bn_relu_res_fwd");
+  if (rc) return rc;
+  PB_REQUIRE(out && bn_coef && y, "pb_bn_relu_res_fwd: null pointer");
+  PB_REQUIRE(ldo >= d && ldo % 4 == 0, "pb_bn_relu_res_fwd: bad ldo");
+  const int64_t total = m * (d / 4);
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
+  cudaStream_t st = as_stream(stream);
+  if (apply_relu) {
+    if (x_res) bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+    else bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+  } else {
+    if (x_res) bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+    else bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+  }
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
+                                  const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
+                                  int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma, float* g_beta,
+                                  float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+  int rc = check_md(m, d, "pb_bn_relu_res_bwd");
+  if (rc) return rc;
+  (void)gamma;
+  PB_REQUIRE(gy && out && save_mean_rstd && bn_coef && g_hi && g_gamma && g_beta && workspace,
+             "pb_bn_relu_res_bwd: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (dtype == PB_F32 && g_lo), "pb_bn_relu_res_bwd: PB_F32 needs g_lo");
+  PB_REQUIRE(ldo >= d && ldo % 4 == 0 && ldg >= d && ldg % 8 == 0, "pb_bn_relu_res_bwd: bad leading dimension");
+  PB_REQUIRE(workspace_bytes >= pb_bn_workspace_bytes(m, d), "pb_bn_relu_res_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int ctas = col_ctas(m);
+  float* partials = reinterpret_cast<float*>(workspace);
+  bn_bwd_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, m, d, partials);
+  PB_LAUNCH_CHECK();
+  col_finalize_kernel<2><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_beta, g_gamma);
+  PB_LAUNCH_CHECK();
+  if (dtype == PB_BF16)
+    bn_bwd_apply_kernel<true><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
+                                                                        g_beta, m, d, g_hi, g_lo, ldg, partials);
+  else
+    bn_bwd_apply_kernel<false><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
+                                                                         g_beta, m, d, g_hi, g_lo, ldg, partials);
+  PB_LAUNCH_CHECK();
+  if (g_bias) {
+    col_finalize_kernel<1><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_bias, nullptr);
+    PB_LAUNCH_CHECK();
+  }
+  return PB_OK;
+}
+
+extern "C" int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d, int32_t dtype, void* g_hi, void* g_lo,
+                            int64_t ldg, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+  int rc = check_md(m, d, "pb_grad_prep");
+  if (rc) return rc;
+  PB_REQUIRE(g && g_hi && workspace, "pb_grad_prep: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (dtype == PB_F32 && g_lo), "pb_grad_prep: PB_F32 needs g_lo");
+  PB_REQUIRE(ldg_in >= d && ldg_in % 4 == 0 && ldg >= d && ldg % 8 == 0, "pb_grad_prep: bad leading dimension");
+  PB_REQUIRE(workspace_bytes >= pb_bn_workspace_bytes(m, d), "pb_grad_prep: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  const int ctas = col_ctas(m);
+  float* partials = reinterpret_cast<float*>(workspace);
+  if (dtype == PB_BF16)
+    grad_prep_kernel<true><<<ctas, kColThreads, col_smem(1, d), st>>>(g, ldg_in, m, d, g_hi, g_lo, ldg, partials);
+  else
+    grad_prep_kernel<false><<<ctas, kColThreads, col_smem(1, d), st>>>(g, ldg_in, m, d, g_hi, g_lo, ldg, partials);
+  PB_LAUNCH_CHECK();
+  if (g_bias) {
+    col_finalize_kernel<1><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_bias, nullptr);
+    PB_LAUNCH_CHECK();
+  }
+  return PB_OK;
+}

@@ -1,0 +1,540 @@
+// tcgen05 tensor-core contractions of the relational graph convolution (sm_100a only).
+//
+// Replaces the 7 N x d x d matmuls of GCL.forward (reference model.py:112,116) and the three matmul
+// families autograd derives from them, each as ONE persistent, warp-specialised kernel:
+//   fwd       out[M,d]  = A[M,K] . Wcat[K,d] + bias      (A K-major,  B = Wcat^T K-major)
+//   bwd-data  dA[M,K]   = g[M,d] . Wcat^T                (A K-major,  B = Wcat   K-major)
+//   bwd-wt    dWcat[K,d]= A^T . g  (split over nodes)    (A MN-major, B MN-major — no transposed copies)
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0    TMA producer: cp.async.bulk.tensor (128B swizzle) into a multi-stage smem ring, mbarrier tx
+//   warp 1    MMA issuer: one lane issues tcgen05.mma (A,B from smem descriptors, D in TMEM, fp32 accumulate),
+//             tcgen05.commit releases smem stages and publishes the accumulator
+//   warps 2-5 epilogue: tcgen05.ld the accumulator (one TMEM lane quadrant per warp), bias / convert, store
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//
+// Precision modes: PB_BF16 -> kind::f16 (bf16 operands), 1 MMA per k-step, tile 128x256x64;
+//                  PB_F32  -> kind::tf32 on TF32 hi/lo splits, 3 MMAs per k-step (hi*hi + hi*lo + lo*hi),
+//                             tile 128x128x32: fp32-grade results from the tensor cores.
+#include <cuda.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
+  if constexpr (BF16) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------------------- descriptors
+// Shared-memory matrix descriptor, 128-byte swizzle, Blackwell version field = 1.
+//   K-major : rows of 128 B along K; 8-row groups every SBO = 1024 B; LBO unused.
+//   MN-major: 128-B lines along M/N, one per k; 8-k groups every SBO = 1024 B; next 128-B-wide M/N chunk at LBO.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, dense, no negate.
+static inline uint32_t make_idesc(bool bf16, int m, int n, int a_mn_major, int b_mn_major) {
+  const uint32_t fmt = bf16 ? 1u : 2u;  // BF16 = 1, TF32 = 2
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct GemmParams {
+  CUtensorMap tm_a[2];   // hi, lo
+  CUtensorMap tm_b[2];
+  int64_t m, n;          // output extent
+  int a_mn_major, b_mn_major;
+  int num_m_tiles, num_n_tiles, num_splits;
+  int k_blocks, k_blocks_per_split;
+  uint32_t idesc;
+  // epilogue
+  void* out;             // fp32 or bf16
+  int64_t ldd;
+  int64_t split_stride;  // elements between split-K partial outputs
+  const float* bias;
+  int out_bf16;
+};
+
+template <bool BF16>
+struct Cfg {
+  static constexpr int kElem = BF16 ? 2 : 4;
+  static constexpr int kSplit = BF16 ? 1 : 2;                // operand arrays (hi[, lo])
+  static constexpr int BM = 128;
+  static constexpr int BN = BF16 ? 256 : 128;
+  static constexpr int BK = 128 / kElem;                     // one 128-byte swizzle row of K
+  static constexpr int UK = 32 / kElem;                      // K per tcgen05.mma
+  static constexpr int kChunk = 128 / kElem;                 // M/N elements per 128-byte line (MN-major)
+  static constexpr int kABytes = BM * 128;                   // one operand tile (per hi/lo array)
+  static constexpr int kBBytes = BN * 128;
+  static constexpr int kStageBytes = kSplit * (kABytes + kBBytes);
+  static constexpr int kStages = BF16 ? 4 : 3;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+constexpr int kGemmThreads = 192;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BF16>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                       // [kStages]
+  uint64_t* empty = bars + C::kStages;         // [kStages]
+  uint64_t* tmem_full = bars + 2 * C::kStages; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < C::kSplit; ++s) { tma_prefetch_desc(&p.tm_a[s]); tma_prefetch_desc(&p.tm_b[s]); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int total_tiles = tiles_mn * p.num_splits;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn, mn = t - split * tiles_mn;
+        const int m0 = (mn / p.num_n_tiles) * C::BM, n0 = (mn % p.num_n_tiles) * C::BN;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty + stage, phase ^ 1);
+          uint8_t* st = smem + stage * C::kStageBytes;
+          mbar_expect_tx(full + stage, C::kStageBytes);
+          const int k0 = kb * C::BK;
+#pragma unroll
+          for (int s = 0; s < C::kSplit; ++s) {
+            uint8_t* sa = st + s * C::kABytes;
+            uint8_t* sb = st + C::kSplit * C::kABytes + s * C::kBBytes;
+            if (p.a_mn_major) {
+#pragma unroll
+              for (int i = 0; i < C::BM / C::kChunk; ++i)   // one 128-byte-wide M chunk per box
+                tma_load_2d(&p.tm_a[s], full + stage, sa + i * (C::BK * 128), m0 + i * C::kChunk, k0);
+            } else {
+              tma_load_2d(&p.tm_a[s], full + stage, sa, k0, m0);
+            }
+            if (p.b_mn_major) {
+#pragma unroll
+              for (int i = 0; i < C::BN / C::kChunk; ++i)
+                tma_load_2d(&p.tm_b[s], full + stage, sb + i * (C::BK * 128), n0 + i * C::kChunk, k0);
+            } else {
+              tma_load_2d(&p.tm_b[s], full + stage, sb, k0, n0);
+            }
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      // descriptor geometry (bytes)
+      const uint32_t a_lbo = p.a_mn_major ? C::BK * 128 : 16, b_lbo = p.b_mn_major ? C::BK * 128 : 16;
+      const uint32_t a_kstep = p.a_mn_major ? C::UK * 128 : 32, b_kstep = p.b_mn_major ? C::UK * 128 : 32;
+      int stage = 0, buf = 0;
+      uint32_t phase = 0, buf_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int split = t / tiles_mn;
+        const int kb0 = split * p.k_blocks_per_split;
+        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        mbar_wait(tmem_empty + buf, buf_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * C::BN;
+        uint32_t accum = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full + stage, phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
+#pragma unroll
+          for (int k = 0; k < C::BK / C::UK; ++k) {
+            const uint32_t a_hi = st + k * a_kstep;
+            const uint32_t b_hi = st + C::kSplit * C::kABytes + k * b_kstep;
+            const uint64_t da_hi = make_smem_desc(a_hi, a_lbo, 1024), db_hi = make_smem_desc(b_hi, b_lbo, 1024);
+            umma<BF16>(d_tmem, da_hi, db_hi, p.idesc, accum);
+            accum = 1;
+            if constexpr (!BF16) {
+              const uint64_t da_lo = make_smem_desc(a_hi + C::kABytes, a_lbo, 1024);
+              const uint64_t db_lo = make_smem_desc(b_hi + C::kBBytes, b_lbo, 1024);
+              umma<BF16>(d_tmem, da_hi, db_lo, p.idesc, 1);
+              umma<BF16>(d_tmem, da_lo, db_hi, p.idesc, 1);
+            }
+          }
+          umma_commit(empty + stage);  // smem stage reusable once these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tmem_full + buf);  // accumulator complete
+        buf ^= 1;
+        if (buf == 0) buf_phase ^= 1;
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int buf = 0;
+    uint32_t buf_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int split = t / tiles_mn, mn = t - split * tiles_mn;
+      const int64_t m0 = (int64_t)(mn / p.num_n_tiles) * C::BM;
+      const int n0 = (mn % p.num_n_tiles) * C::BN;
+      mbar_wait(tmem_full + buf, buf_phase);
+      tc_fence_after();
+      const int64_t row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.m;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C::BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * C::BN + c0), v);
+        const int col = n0 + c0;
+        if (row_ok && col < p.n) {   // n is a multiple of 32 (host check): whole 32-column chunk in range
+          if (p.out_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)split * p.split_stride +
+                               (size_t)row * p.ldd + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 q;
+              q.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              q.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              q.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              q.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              *reinterpret_cast<uint4*>(o + j) = q;
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)row * p.ldd + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 q = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (p.bias) {
+                const float4 b = ldg4(p.bias + col + j);
+                q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+              }
+              *reinterpret_cast<float4*>(o + j) = q;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + buf);
+      buf ^= 1;
+      if (buf == 0) buf_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// fixed-order reduction of split-K partials: out[i] = sum_s part[s][i]
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int n_splits, int64_t n_elems,
+                                     float* __restrict__ out) {
+  const int64_t n4 = n_elems >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = ldg4(part + 4 * i);
+    for (int k = 1; k < n_splits; ++k) {
+      const float4 v = ldg4(part + (size_t)k * n_elems + 4 * i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// Operand stored row-major as [rows, cols] with leading dimension ld (elements).
+//   K-major use : rows = M/N index, cols = K          -> 2-D map {K, rows}, box {BK, box_rows}
+//   MN-major use: rows = K index,  cols = M/N index   -> 2-D map {cols, K}, box {128-byte chunk, BK}; one box
+//                                                        per chunk lands at chunk*BK*128 (the descriptor's LBO)
+static int make_map(CUtensorMap* map, const void* ptr, bool bf16, bool mn_major, int64_t rows, int64_t cols, int64_t ld,
+                    int box_mn, int bk) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled unavailable (driver entry point lookup failed)");
+    return PB_ERR_CUDA;
+  }
+  const int es = bf16 ? 2 : 4;
+  const CUtensorMapDataType dt = bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r;
+  if (!mn_major) {
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_mn};
+    cuuint32_t estr[2] = {1, 1};
+    r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const int chunk = 128 / es;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * es};
+    cuuint32_t box[2] = {(cuuint32_t)chunk, (cuuint32_t)bk};
+    cuuint32_t estr[2] = {1, 1};
+    r = fn(map, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld mn_major=%d)", (int)r,
+              (long long)rows, (long long)cols, (long long)ld, (int)mn_major);
+    return PB_ERR_CUDA;
+  }
+  return PB_OK;
+}
+
+struct Operand {
+  const void* hi;
+  const void* lo;
+  int64_t rows, cols, ld;  // storage shape (row-major)
+  bool mn_major;
+};
+
+template <bool BF16>
+static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n, int64_t k, void* out, int64_t ldd,
+                       bool out_bf16, const float* bias, int num_splits, int64_t split_stride, cudaStream_t st) {
+  using C = Cfg<BF16>;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  for (int s = 0; s < C::kSplit; ++s) {
+    rc = make_map(&p.tm_a[s], s ? a.lo : a.hi, BF16, a.mn_major, a.rows, a.cols, a.ld, C::BM, C::BK);
+    if (rc) return rc;
+    rc = make_map(&p.tm_b[s], s ? b.lo : b.hi, BF16, b.mn_major, b.rows, b.cols, b.ld, C::BN, C::BK);
+    if (rc) return rc;
+  }
+  p.m = m;
+  p.n = n;
+  p.a_mn_major = a.mn_major;
+  p.b_mn_major = b.mn_major;
+  p.num_m_tiles = (int)((m + C::BM - 1) / C::BM);
+  p.num_n_tiles = (int)((n + C::BN - 1) / C::BN);
+  p.k_blocks = (int)((k + C::BK - 1) / C::BK);
+  num_splits = std::max(1, std::min(num_splits, p.k_blocks));
+  p.k_blocks_per_split = (p.k_blocks + num_splits - 1) / num_splits;
+  p.num_splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  p.idesc = make_idesc(BF16, C::BM, C::BN, a.mn_major, b.mn_major);
+  p.out = out;
+  p.ldd = ldd;
+  p.split_stride = split_stride;
+  p.bias = bias;
+  p.out_bf16 = out_bf16;
+  const int64_t total = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_splits;
+  const int grid = (int)std::min<int64_t>(total, sm_count());
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set = true;
+  }
+  gemm_tcgen05_kernel<BF16><<<grid, kGemmThreads, C::kSmemBytes, st>>>(p);
+  PB_LAUNCH_CHECK();
+  return p.num_splits;  // > 0
+}
+
+static int check_gemm_dims(int64_t m, int d, int k, int dtype, const char* who) {
+  PB_REQUIRE(m > 0 && m < ((int64_t)1 << 31), "%s: m out of range", who);
+  PB_REQUIRE(d >= 64 && d % 64 == 0 && d <= 1024, "%s: d=%d must be a multiple of 64 in [64, 1024]", who, d);
+  PB_REQUIRE(k >= 64 && k % 64 == 0, "%s: k=%d must be a multiple of 64", who, k);
+  PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "%s: bad dtype", who);
+  return PB_OK;
+}
+
+static int bwd_weight_splits(int64_t m, int d, int k, bool bf16) {
+  const int bm = 128, bn = bf16 ? 256 : 128, bk = bf16 ? 64 : 32;
+  const int64_t tiles = (int64_t)((k + bm - 1) / bm) * ((d + bn - 1) / bn);
+  const int64_t kblocks = (m + bk - 1) / bk;
+  int64_t s = (3 * (int64_t)148 + tiles - 1) / tiles;       // ~3 waves of work items
+  s = std::max<int64_t>(1, std::min<int64_t>(s, std::min<int64_t>(kblocks, 64)));
+  return (int)s;
+}
+
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                                const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
+                                int32_t k, int32_t dtype, pb_stream_t stream) {
+  int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_fwd");
+  if (rc) return rc;
+  PB_REQUIRE(a_hi && wcat_t_hi && out, "pb_rgcn_gemm_fwd: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (a_lo && wcat_t_lo), "pb_rgcn_gemm_fwd: PB_F32 needs lo operands");
+  PB_REQUIRE(lda >= k && lda % 8 == 0 && ldo >= d && ldo % 4 == 0, "pb_rgcn_gemm_fwd: bad leading dimension");
+  Operand a{a_hi, a_lo, m, k, lda, false};
+  Operand b{wcat_t_hi, wcat_t_lo, d, k, k, false};
+  cudaStream_t st = as_stream(stream);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st)
+                        : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st);
+  return rc < 0 ? rc : PB_OK;
+}
+
+extern "C" int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
+                                     const void* wcat_lo, void* d_a, int64_t ldda, int64_t m, int32_t d, int32_t k,
+                                     int32_t dtype, pb_stream_t stream) {
+  int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_bwd_data");
+  if (rc) return rc;
+  PB_REQUIRE(g_hi && wcat_hi && d_a, "pb_rgcn_gemm_bwd_data: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (g_lo && wcat_lo), "pb_rgcn_gemm_bwd_data: PB_F32 needs lo operands");
+  PB_REQUIRE(ldg >= d && ldg % 8 == 0 && ldda >= k && ldda % 8 == 0, "pb_rgcn_gemm_bwd_data: bad leading dimension");
+  Operand a{g_hi, g_lo, m, d, ldg, false};          // [M, d], contraction over d
+  Operand b{wcat_hi, wcat_lo, k, d, d, false};      // Wcat [K, d]: rows = output columns, K-major in d
+  cudaStream_t st = as_stream(stream);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, k, d, d_a, ldda, true, nullptr, 1, 0, st)
+                        : launch_gemm<false>(a, b, m, k, d, d_a, ldda, false, nullptr, 1, 0, st);
+  return rc < 0 ? rc : PB_OK;
+}
+
+extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k) {
+  if (m <= 0 || d <= 0 || k <= 0) return 0;
+  const int s = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false));
+  return align_up((size_t)s * k * d * sizeof(float), 256);
+}
+
+extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
+                                       const void* g_lo, int64_t ldg, float* d_wcat, int64_t m, int32_t d, int32_t k,
+                                       int32_t dtype, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+  int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_bwd_weight");
+  if (rc) return rc;
+  PB_REQUIRE(a_hi && g_hi && d_wcat && workspace, "pb_rgcn_gemm_bwd_weight: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (a_lo && g_lo), "pb_rgcn_gemm_bwd_weight: PB_F32 needs lo operands");
+  PB_REQUIRE(lda >= k && lda % 8 == 0 && ldg >= d && ldg % 8 == 0, "pb_rgcn_gemm_bwd_weight: bad leading dimension");
+  PB_REQUIRE(workspace_bytes >= pb_rgcn_gemm_bwd_weight_workspace_bytes(m, d, k), "pb_rgcn_gemm_bwd_weight: workspace too small");
+  const bool bf16 = dtype == PB_BF16;
+  const int splits = bwd_weight_splits(m, d, k, bf16);
+  Operand a{a_hi, a_lo, m, k, lda, true};   // stored [nodes, K]: output rows (K) contiguous -> MN-major
+  Operand b{g_hi, g_lo, m, d, ldg, true};   // stored [nodes, d]
+  cudaStream_t st = as_stream(stream);
+  float* part = reinterpret_cast<float*>(workspace);
+  const int64_t n_elems = (int64_t)k * d;
+  rc = bf16 ? launch_gemm<true>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st)
+            : launch_gemm<false>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+  if (rc < 0) return rc;
+  const int used = rc;
+  const unsigned grid = (unsigned)std::min<int64_t>((n_elems / 4 + 255) / 256, (int64_t)sm_count() * 8);
+  splitk_reduce_kernel<<<grid, 256, 0, st>>>(part, used, n_elems, d_wcat);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

@@ -1,0 +1,222 @@
+"""Batched on-device graph construction and CSR plans.
+
+Host-side mirror of the reference's ``graph_from_tensor`` (data.py:141-204) and of the per-sequence loop +
+``Batch.from_data_list`` in ``Decoder._structure_from_binary`` (model.py:596-607): same attribute names
+(``edge_index, edge_attrs, node_features, is_drum, bars, batch, num_nodes``), same values bit for bit, same
+in-place fake activation of empty bars — but the whole batch is built by two CUDA kernels
+(pb_graph_count / pb_graph_fill) instead of Python loops, and ``edge_attrs`` (E x 33 fp32) is only
+materialised if somebody asks for it.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _ffi
+
+N_TRACKS = 4
+N_TIMESTEPS = 32
+
+
+class CsrPlan:
+    """Destination-/source-sorted views of an edge list (pb_csr_build); shared by all layers of a GCN."""
+
+    def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, edge_dist: torch.Tensor,
+                 num_nodes: int, n_relations: int = _ffi.N_RELATIONS):
+        _ffi.require_cuda(edge_index, edge_type, edge_dist)
+        if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise ValueError("edge_index must be int64 [2, E]")
+        edge_index = edge_index.contiguous()
+        edge_type = edge_type.contiguous()
+        edge_dist = edge_dist.contiguous()
+        if edge_type.dtype != torch.uint8 or edge_dist.dtype != torch.uint8:
+            raise ValueError("edge_type / edge_dist must be uint8")
+        dev = edge_index.device
+        n, e, r = int(num_nodes), int(edge_index.size(1)), int(n_relations)
+        lib = _ffi.lib()
+        self.n_nodes, self.n_edges, self.n_relations = n, e, r
+        self.in_ptr = torch.empty(n * r + 1, dtype=torch.int32, device=dev)
+        self.in_edge = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        self.in_eid = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        self.out_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        self.out_rec = torch.empty((max(e, 1), 4), dtype=torch.int32, device=dev)
+        ws_bytes = lib.pb_csr_workspace_bytes(n, e, r)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _ffi.check(lib.pb_csr_build(edge_index.data_ptr(), edge_type.data_ptr(), edge_dist.data_ptr(), n, e, r,
+                                        self.in_ptr.data_ptr(), self.in_edge.data_ptr(), self.in_eid.data_ptr(),
+                                        self.out_ptr.data_ptr(), self.out_rec.data_ptr(), ws.data_ptr(), ws_bytes,
+                                        _ffi.stream()), "pb_csr_build")
+        self.device = dev
+        self.struct = _ffi.CsrStruct(n, e, r, 0, self.in_ptr.data_ptr(), self.in_edge.data_ptr(),
+                                     self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr())
+
+    def ref(self):
+        return ctypes.byref(self.struct)
+
+
+class Graph:
+    """Attribute bag with the fields of the reference's PyG ``Data``/``Batch`` for this path."""
+
+    def __init__(self, **kwargs):
+        self._edge_attrs = None
+        self._plan = None
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    # edge_attrs f32 [E, 33] (data.py:179-182) is derived data: built on first access
+    @property
+    def edge_attrs(self) -> torch.Tensor:
+        if self._edge_attrs is None:
+            e = self.edge_type.numel()
+            out = torch.empty((e, N_TIMESTEPS + 1), dtype=torch.float32, device=self.edge_type.device)
+            with torch.cuda.device(out.device):
+                _ffi.check(_ffi.lib().pb_edge_attrs_encode(self.edge_type.data_ptr(), self.edge_dist.data_ptr(), e,
+                                                           out.data_ptr(), _ffi.stream()), "pb_edge_attrs_encode")
+            self._edge_attrs = out
+        return self._edge_attrs
+
+    @edge_attrs.setter
+    def edge_attrs(self, value):
+        self._edge_attrs = value
+        self._plan = None
+
+    @property
+    def plan(self) -> CsrPlan:
+        if self._plan is None:
+            self._plan = CsrPlan(self.edge_index, self.edge_type, self.edge_dist, self.num_nodes)
+        return self._plan
+
+    @property
+    def keys(self):
+        return [k for k in self.__dict__ if not k.startswith("_")] + ["edge_attrs"]
+
+    def to(self, device, *args, **kwargs):
+        device = torch.device(device)
+        for k, v in list(self.__dict__.items()):
+            if isinstance(v, torch.Tensor) and v.device != device:
+                if k.startswith("_"):
+                    setattr(self, k, None)
+                else:
+                    setattr(self, k, v.to(device, *args, **kwargs))
+        if self._plan is not None and self._plan.device != device:
+            self._plan = None
+        return self
+
+
+def _as_device_bytes(s_tensor: torch.Tensor, device: Optional[torch.device]):
+    """Returns (uint8 view on CUDA sharing storage when possible, write-back target or None)."""
+    if s_tensor.dtype not in (torch.bool, torch.uint8):
+        raise ValueError("s_tensor must be a bool/uint8 structure tensor")
+    if s_tensor.size(-1) != N_TIMESTEPS or s_tensor.size(-2) != N_TRACKS:
+        raise ValueError(f"s_tensor must end in [{N_TRACKS}, {N_TIMESTEPS}], got {tuple(s_tensor.shape)}")
+    if s_tensor.is_cuda and s_tensor.is_contiguous():
+        return s_tensor.view(torch.uint8), None
+    if device is None:
+        device = s_tensor.device if s_tensor.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    if not torch.cuda.is_available():
+        raise _ffi.PolyphemusB200Error("graph construction runs on the GPU only (no CPU fallback)")
+    dev_copy = s_tensor.to(device).contiguous()
+    return dev_copy.view(torch.uint8), s_tensor
+
+
+def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = None,
+                       with_edge_attrs: bool = False) -> Graph:
+    """s_tensor bool [B, n_bars, 4, 32] -> one batched graph (== Batch.from_data_list of per-sequence graphs).
+
+    Empty bars get the fake activation ``s[b, bar, 0, 0] = True`` in the caller's tensor, exactly as
+    data.py:152-153 does. One host sync (the {N, E} read-back that sizes the outputs).
+    """
+    if s_tensor.dim() != 4:
+        raise ValueError("expected s_tensor of shape [B, n_bars, 4, 32]")
+    bsz, n_bars = int(s_tensor.size(0)), int(s_tensor.size(1))
+    s_u8, write_back = _as_device_bytes(s_tensor, device)
+    dev = s_u8.device
+    lib = _ffi.lib()
+    total_bars = bsz * n_bars
+    with torch.cuda.device(dev):
+        st = _ffi.stream()
+        bar_bits = torch.empty((total_bars, 4), dtype=torch.int32, device=dev)
+        node_ptr = torch.empty(total_bars + 1, dtype=torch.int32, device=dev)
+        edge_ptr = torch.empty(total_bars + 1, dtype=torch.int32, device=dev)
+        totals = torch.empty(4, dtype=torch.int64, device=dev)
+        ws_bytes = lib.pb_graph_workspace_bytes(total_bars)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _ffi.check(lib.pb_graph_count(s_u8.data_ptr(), total_bars, bar_bits.data_ptr(), node_ptr.data_ptr(),
+                                      edge_ptr.data_ptr(), totals.data_ptr(), ws.data_ptr(), ws_bytes, st),
+                   "pb_graph_count")
+        n, e, n_drum, _ = (int(v) for v in totals.tolist())          # the one host sync
+        edge_index = torch.empty((2, e), dtype=torch.int64, device=dev)
+        edge_type = torch.empty(e, dtype=torch.uint8, device=dev)
+        edge_dist = torch.empty(e, dtype=torch.uint8, device=dev)
+        edge_attrs = torch.empty((e, N_TIMESTEPS + 1), dtype=torch.float32, device=dev) if with_edge_attrs else None
+        node_features = torch.empty((n, N_TRACKS), dtype=torch.float32, device=dev)
+        is_drum = torch.empty(n, dtype=torch.bool, device=dev)
+        bars = torch.empty(n, dtype=torch.int64, device=dev)
+        batch = torch.empty(n, dtype=torch.int64, device=dev)
+        node_track = torch.empty(n, dtype=torch.uint8, device=dev)
+        _ffi.check(lib.pb_graph_fill(bar_bits.data_ptr(), node_ptr.data_ptr(), edge_ptr.data_ptr(), total_bars, n_bars,
+                                     edge_index.data_ptr(), e, edge_type.data_ptr(), edge_dist.data_ptr(),
+                                     _ffi.ptr(edge_attrs), node_features.data_ptr(), is_drum.data_ptr(),
+                                     bars.data_ptr(), batch.data_ptr(), node_track.data_ptr(), st), "pb_graph_fill")
+    if write_back is not None:
+        write_back.copy_(s_u8.view(write_back.dtype).reshape(write_back.shape))
+    g = Graph(edge_index=edge_index, edge_type=edge_type, edge_dist=edge_dist, node_features=node_features,
+              is_drum=is_drum, bars=bars, batch=batch, num_nodes=n, num_edges=e, num_graphs=bsz, n_bars=n_bars,
+              n_drum=n_drum, node_track=node_track, bar_ptr=node_ptr)
+    if edge_attrs is not None:
+        g._edge_attrs = edge_attrs
+    return g
+
+
+def graph_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = None) -> Graph:
+    """Drop-in for ``data.graph_from_tensor`` (data.py:141): one sequence ``[n_bars, 4, 32]``.
+
+    As in the reference, ``graph.batch`` and ``graph.bars`` both hold the bar index of each node.
+    """
+    if s_tensor.dim() != 3:
+        raise ValueError("expected s_tensor of shape [n_bars, 4, 32]")
+    g = graphs_from_tensor(s_tensor.unsqueeze(0), device=device)
+    g.batch = g.bars
+    return g
+
+
+def plan_for(data, num_nodes: Optional[int] = None) -> CsrPlan:
+    """CSR plan for whatever GCN/GCL was handed: our own Graph, or a foreign PyG-style object."""
+    if isinstance(data, Graph):
+        return data.plan
+    cached = getattr(data, "_pb_plan", None)
+    if cached is not None:
+        return cached
+    edge_attrs = data.edge_attrs
+    edge_type, edge_dist = decode_edge_attrs(edge_attrs[:, 0], edge_attrs[:, 1:])
+    n = int(num_nodes if num_nodes is not None else data.x.size(0))
+    plan = CsrPlan(data.edge_index, edge_type, edge_dist, n)
+    try:
+        data._pb_plan = plan
+    except Exception:
+        pass
+    return plan
+
+
+def decode_edge_attrs(edge_type: torch.Tensor, edge_attr: torch.Tensor):
+    """float edge_type [E] + one-hot edge_attr [E, 32] (model.py:193-194) -> uint8 type, uint8 distance."""
+    _ffi.require_cuda(edge_type, edge_attr)
+    if edge_attr.dim() != 2 or edge_attr.size(1) != _ffi.N_DISTS:
+        raise ValueError("edge_attr must be [E, 32] one-hot timestep distances")
+    edge_type = edge_type.float()
+    edge_attr = edge_attr.float()
+    if edge_attr.stride(1) != 1:
+        edge_attr = edge_attr.contiguous()
+    e = int(edge_attr.size(0))
+    dev = edge_attr.device
+    t_out = torch.empty(e, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(e, dtype=torch.uint8, device=dev)
+    if e:
+        with torch.cuda.device(dev):
+            _ffi.check(_ffi.lib().pb_edge_attrs_decode(edge_type.data_ptr(), edge_type.stride(0), edge_attr.data_ptr(),
+                                                       edge_attr.stride(0), e, t_out.data_ptr(), d_out.data_ptr(),
+                                                       _ffi.stream()), "pb_edge_attrs_decode")
+    return t_out, d_out

@@ -1,0 +1,236 @@
+"""Autograd bindings of the message-passing kernels (thin host glue over the C ABI).
+
+One ``torch.autograd.Function`` covers a whole GCN layer of the reference (model.py:198-206):
+
+    out = GCL(x)            model.py:55-121   pb_edge_table_fwd, pb_agg_fwd, pb_weight_prep, pb_rgcn_gemm_fwd
+    y   = x_res + relu(BN(out))               pb_bn_stats, pb_bn_relu_res_fwd
+
+and its backward (what autograd derives for those lines in the reference):
+
+    pb_bn_relu_res_bwd -> pb_agg_fwd (operand recompute) -> pb_rgcn_gemm_bwd_weight, pb_rgcn_gemm_bwd_data
+    -> pb_agg_bwd -> pb_edge_table_bwd
+
+PyTorch only owns the memory and the stream here; no arithmetic of the path runs in ATen.
+"""
+from __future__ import annotations
+
+import itertools
+import threading
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _ffi
+from .graph import CsrPlan
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+_state = threading.local()
+_PRECISIONS = {"fp32": _ffi.PB_F32, "bf16": _ffi.PB_BF16}
+_default_precision = "fp32"
+_seed_counter = itertools.count()
+
+# every C-ABI kernel launch is counted so that bench.py can report `gpu_launches` from the product itself
+launch_counter = {"n": 0}
+
+# kernel launches per ABI call (see csrc/*.cu); used only for the counter above
+_LAUNCHES = {
+    "pb_edge_table_fwd": 1, "pb_agg_fwd": 1, "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_bn_stats": 2,
+    "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1, "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,
+    "pb_rgcn_gemm_bwd_weight": 2, "pb_rgcn_gemm_bwd_data": 1, "pb_agg_bwd": 1, "pb_edge_table_bwd": 1,
+}
+
+
+def set_precision(name: str) -> None:
+    """'fp32' (TF32x3 tensor-core mode, fp32-grade) or 'bf16' (bf16 operands, fp32 accumulate)."""
+    global _default_precision
+    if name not in _PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+    _default_precision = name
+
+
+def get_precision() -> str:
+    return _default_precision
+
+
+def _call(name: str, *args) -> None:
+    _ffi.check(getattr(_ffi.lib(), name)(*args), name)
+    launch_counter["n"] += _LAUNCHES.get(name, 1)
+
+
+def next_seed() -> int:
+    """Per-call dropout seed: deterministic under torch.manual_seed and call order, no device sync."""
+    base = torch.initial_seed() & 0xFFFFFFFFFFFFFFFF
+    return (base * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+
+
+@dataclass
+class LayerConfig:
+    dtype: int                 # _ffi.PB_F32 / PB_BF16
+    p_drop: float              # GCL message dropout (model.py:133)
+    seed: int
+    training: bool
+    batch_norm: bool           # fuse BN + ReLU + residual (GCN layer) or return the raw GCL output
+    eps: float = BN_EPS
+    momentum: float = BN_MOMENTUM
+
+
+def _operand(n: int, k: int, dtype: int, dev):
+    """GEMM operand buffers in the arithmetic mode's storage: bf16, or TF32 hi/lo fp32 pair."""
+    if dtype == _ffi.PB_BF16:
+        return torch.empty((n, k), dtype=torch.bfloat16, device=dev), None
+    return torch.empty((n, k), dtype=torch.float32, device=dev), torch.empty((n, k), dtype=torch.float32, device=dev)
+
+
+def _edge_table(nn_w: torch.Tensor, nn_b: torch.Tensor, d: int, st: int) -> torch.Tensor:
+    table = torch.empty((_ffi.N_DISTS, d), dtype=torch.float32, device=nn_w.device)
+    _call("pb_edge_table_fwd", nn_w.data_ptr(), nn_b.data_ptr(), d, table.data_ptr(), st)
+    return table
+
+
+def _weights(weight, root, r, d, dtype, st):
+    dev = weight.device
+    k = (r + 1) * d
+    tdt = torch.bfloat16 if dtype == _ffi.PB_BF16 else torch.float32
+    w_hi = torch.empty((k, d), dtype=tdt, device=dev)
+    wt_hi = torch.empty((d, k), dtype=tdt, device=dev)
+    w_lo = wt_lo = None
+    if dtype == _ffi.PB_F32:
+        w_lo, wt_lo = torch.empty_like(w_hi), torch.empty_like(wt_hi)
+    _call("pb_weight_prep", weight.data_ptr(), root.data_ptr(), r, d, dtype, w_hi.data_ptr(), _ffi.ptr(w_lo),
+          wt_hi.data_ptr(), _ffi.ptr(wt_lo), st)
+    return w_hi, w_lo, wt_hi, wt_lo
+
+
+class RGCLayerFn(torch.autograd.Function):
+    """y = x_res + relu(BN(GCL(x)))   (cfg.batch_norm)   or   y = GCL(x)   (plain layer)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var,
+                plan: CsrPlan, cfg: LayerConfig):
+        _ffi.require_cuda(x, weight, root, nn_w, nn_b)
+        if x.dtype != torch.float32:
+            raise TypeError("node features must be float32 (the arithmetic mode is chosen by `precision`)")
+        x = x.contiguous()
+        n, d = x.shape
+        r = plan.n_relations
+        if weight.shape != (r, d, d) or root.shape != (d, d):
+            raise ValueError("the CUDA path supports in_channels == out_channels == d, weight [R,d,d], root [d,d]")
+        if n != plan.n_nodes:
+            raise ValueError(f"x has {n} rows but the graph has {plan.n_nodes} nodes")
+        k = (r + 1) * d
+        dev = x.device
+        weight, root = weight.contiguous(), root.contiguous()
+        nn_w, nn_b = nn_w.contiguous(), nn_b.contiguous()
+        bias_c = None if bias is None else bias.contiguous()
+        with torch.cuda.device(dev):
+            st = _ffi.stream()
+            table = _edge_table(nn_w, nn_b, d, st)
+            a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
+            p = cfg.p_drop if cfg.training else 0.0
+            _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
+                  cfg.dtype, p, cfg.seed, st)
+            _, _, wt_hi, wt_lo = _weights(weight, root, r, d, cfg.dtype, st)
+            out = torch.empty((n, d), dtype=torch.float32, device=dev)
+            _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
+                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, cfg.dtype, st)
+            if not cfg.batch_norm:
+                ctx.save_for_backward(x, weight, root, nn_w, nn_b)
+                ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
+                return out
+            coef = torch.empty((3, d), dtype=torch.float32, device=dev)
+            save = torch.empty((2, d), dtype=torch.float32, device=dev)
+            if cfg.training:
+                ws_bytes = _ffi.lib().pb_bn_workspace_bytes(n, d)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _call("pb_bn_stats", out.data_ptr(), d, n, d, gamma.data_ptr(), beta.data_ptr(), cfg.eps, cfg.momentum,
+                      _ffi.ptr(running_mean), _ffi.ptr(running_var), save.data_ptr(), coef.data_ptr(), ws.data_ptr(),
+                      ws_bytes, st)
+            else:
+                _call("pb_bn_prepare_eval", gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
+                      running_var.data_ptr(), cfg.eps, d, coef.data_ptr(), st)
+            y = torch.empty((n, d), dtype=torch.float32, device=dev)
+            _call("pb_bn_relu_res_fwd", out.data_ptr(), d, x.data_ptr(), coef.data_ptr(), y.data_ptr(), n, d, 1, st)
+        ctx.save_for_backward(x, weight, root, nn_w, nn_b, gamma, out, coef, save)
+        ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        cfg: LayerConfig = ctx.cfg
+        plan: CsrPlan = ctx.plan
+        if cfg.batch_norm and not cfg.training:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not part of the training path")
+        gy = gy.contiguous()
+        if cfg.batch_norm:
+            x, weight, root, nn_w, nn_b, gamma, out, coef, save = ctx.saved_tensors
+        else:
+            x, weight, root, nn_w, nn_b = ctx.saved_tensors
+        n, d = x.shape
+        r = plan.n_relations
+        k = (r + 1) * d
+        dev = x.device
+        lib = _ffi.lib()
+        with torch.cuda.device(dev):
+            st = _ffi.stream()
+            g_hi, g_lo = _operand(n, d, cfg.dtype, dev)
+            g_bias = torch.empty(d, dtype=torch.float32, device=dev)
+            ws_bytes = lib.pb_bn_workspace_bytes(n, d)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            g_gamma = g_beta = None
+            if cfg.batch_norm:
+                g_gamma = torch.empty(d, dtype=torch.float32, device=dev)
+                g_beta = torch.empty(d, dtype=torch.float32, device=dev)
+                _call("pb_bn_relu_res_bwd", gy.data_ptr(), out.data_ptr(), d, gamma.data_ptr(), save.data_ptr(),
+                      coef.data_ptr(), n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d, g_gamma.data_ptr(),
+                      g_beta.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
+            else:
+                _call("pb_grad_prep", gy.data_ptr(), d, n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
+                      g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
+            # recompute the aggregated operand instead of keeping N x (R+1)d per layer alive
+            table = _edge_table(nn_w, nn_b, d, st)
+            a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
+            p = cfg.p_drop if cfg.training else 0.0
+            _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
+                  cfg.dtype, p, cfg.seed, st)
+            w_hi, w_lo, _, _ = _weights(weight, root, r, d, cfg.dtype, st)
+            d_wcat = torch.empty((k, d), dtype=torch.float32, device=dev)
+            wws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, d, k)
+            wws = torch.empty(wws_bytes, dtype=torch.uint8, device=dev)
+            _call("pb_rgcn_gemm_bwd_weight", a_hi.data_ptr(), _ffi.ptr(a_lo), k, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
+                  d_wcat.data_ptr(), n, d, k, cfg.dtype, wws.data_ptr(), wws_bytes, st)
+            del a_hi, a_lo, wws
+            d_a = torch.empty((n, k), dtype=torch.bfloat16 if cfg.dtype == _ffi.PB_BF16 else torch.float32, device=dev)
+            _call("pb_rgcn_gemm_bwd_data", g_hi.data_ptr(), _ffi.ptr(g_lo), d, w_hi.data_ptr(), _ffi.ptr(w_lo),
+                  d_a.data_ptr(), k, n, d, k, cfg.dtype, st)
+            gx = torch.empty((n, d), dtype=torch.float32, device=dev)
+            n_part = lib.pb_agg_bwd_num_partials()
+            partials = torch.empty((n_part, _ffi.N_DISTS, d), dtype=torch.float32, device=dev)
+            _call("pb_agg_bwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
+                  gy.data_ptr() if cfg.batch_norm else None, gx.data_ptr(), partials.data_ptr(), p, cfg.seed, st)
+            g_nn_w = torch.empty((d, _ffi.N_DISTS), dtype=torch.float32, device=dev)
+            g_nn_b = torch.empty(d, dtype=torch.float32, device=dev)
+            _call("pb_edge_table_bwd", partials.data_ptr(), n_part, d, g_nn_w.data_ptr(), g_nn_b.data_ptr(), st)
+        g_weight = d_wcat[: r * d].view(r, d, d)
+        g_root = d_wcat[r * d:]
+        return (gx, g_weight, g_root, g_bias if ctx.has_bias else None, g_nn_w, g_nn_b, g_gamma, g_beta,
+                None, None, None, None)
+
+
+def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, beta=None, running_mean=None,
+              running_var=None, batch_norm: bool, training: bool, p_drop: float, precision: Optional[str] = None,
+              seed: Optional[int] = None, eps: float = BN_EPS, momentum: float = BN_MOMENTUM):
+    cfg = LayerConfig(dtype=_PRECISIONS[precision or _default_precision], p_drop=float(p_drop),
+                      seed=next_seed() if seed is None else int(seed), training=bool(training),
+                      batch_norm=bool(batch_norm), eps=float(eps), momentum=float(momentum))
+    return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg)
+
+
+def dropout_keep_mask(n_edges: int, d: int, p_drop: float, seed: int, device) -> torch.Tensor:
+    """The keep-mask pb_agg_fwd/bwd use for (seed, p): bool [E, d], indexed by edge_index column."""
+    keep = torch.empty((n_edges, d), dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        _call("pb_dropout_mask", n_edges, d, float(p_drop), int(seed), keep.data_ptr(), _ffi.stream())
+    return keep.bool()

@@ -1,0 +1,291 @@
+"""The Polyphemus graph VAE around the CUDA message-passing path (host side, plain PyTorch).
+
+Only the two ``GCN`` stacks and the graph construction are the hot path; everything in this
+file is the *caller* of that path and stays ordinary PyTorch. It keeps the reference's drop-in surface
+(model.py:138-678): constructor kwargs (``VAE(**training.json["model"], device=...)``), forward signatures,
+module/attribute names and therefore state-dict keys (255 at the published config, checked against
+tests/golden/state_dict_keys.json), and the order in which parameters are created and re-initialised, so a
+given ``torch.manual_seed`` produces the reference's initial weights.
+
+Differences from the reference are confined to *how* the same values are produced:
+  * boolean-mask indexing (a host sync per mask, model.py:352-353,396-397,552-553,575-576) is replaced by
+    index tensors that the device graph builder already knows the sizes of;
+  * ``torch.unique`` + ``repeat_interleave`` (model.py:543-545) becomes one ``index_select``;
+  * graph building inside ``Decoder`` (model.py:596-607) is one batched kernel call instead of a Python
+    loop over sequences and bars.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .conv import GCN, _reset
+from .graph import Graph, graphs_from_tensor
+
+N_TRACKS = 4
+N_PITCH_TOKENS = 131
+N_DUR_TOKENS = 99
+D_TOKEN_PAIR = N_PITCH_TOKENS + N_DUR_TOKENS
+MAX_SIMU_TOKENS = 16
+N_EDGE_TYPES = N_TRACKS + 2
+
+
+class MLP(nn.Module):
+    def __init__(self, input_dim=256, hidden_dim=256, output_dim=256, num_layers=2, activation=True, dropout=0.1):
+        super().__init__()
+        widths = [input_dim] + [hidden_dim] * (num_layers - 1) + [output_dim]
+        self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(widths[:-1], widths[1:]))
+        self.activation = activation
+        self.p = dropout
+
+    def forward(self, x):
+        for lin in self.layers:
+            x = lin(F.dropout(x, p=self.p, training=self.training))
+            if self.activation:
+                x = F.relu(x)
+        return x
+
+
+class CNNEncoder(nn.Module):
+    """[*, 4, 32] structure bar -> vector (model.py:211-256); Sequential indices match the reference keys."""
+
+    def __init__(self, output_dim=256, dense_dim=256, batch_norm=False, dropout=0.1):
+        super().__init__()
+        conv = [nn.Conv2d(1, 8, 3, padding=1)]
+        if batch_norm:
+            conv.append(nn.BatchNorm2d(8))
+        conv += [nn.ReLU(True), nn.MaxPool2d((1, 4), stride=(1, 4)), nn.Conv2d(8, 16, 3, padding=1)]
+        if batch_norm:
+            conv.append(nn.BatchNorm2d(16))
+        conv.append(nn.ReLU(True))
+        self.conv = nn.Sequential(*conv)
+        self.flatten = nn.Flatten(start_dim=1)
+        self.lin = nn.Sequential(nn.Dropout(dropout), nn.Linear(16 * 4 * 8, dense_dim), nn.ReLU(True),
+                                 nn.Dropout(dropout), nn.Linear(dense_dim, output_dim))
+
+    def forward(self, x):
+        return self.lin(self.flatten(self.conv(x.unsqueeze(1))))
+
+
+class CNNDecoder(nn.Module):
+    """vector -> [*, 1, 1, 4, 32] structure logits (model.py:259-299)."""
+
+    def __init__(self, input_dim=256, dense_dim=256, batch_norm=False, dropout=0.1):
+        super().__init__()
+        self.lin = nn.Sequential(nn.Dropout(dropout), nn.Linear(input_dim, dense_dim), nn.ReLU(True),
+                                 nn.Dropout(dropout), nn.Linear(dense_dim, 16 * 4 * 8), nn.ReLU(True))
+        self.unflatten = nn.Unflatten(dim=1, unflattened_size=(16, 4, 8))
+        conv = [nn.Upsample(scale_factor=(1, 4), mode="nearest"), nn.Conv2d(16, 8, 3, padding=1)]
+        if batch_norm:
+            conv.append(nn.BatchNorm2d(8))
+        conv += [nn.ReLU(True), nn.Conv2d(8, 1, 3, padding=1)]
+        self.conv = nn.Sequential(*conv)
+
+    def forward(self, x):
+        return self.conv(self.unflatten(self.lin(x))).unsqueeze(1)
+
+
+class GlobalAttention(nn.Module):
+    """Soft-attention pooling over the nodes of each bar (PyG GlobalAttention, model.py:335-340,409)."""
+
+    def __init__(self, gate_nn: nn.Module):
+        super().__init__()
+        self.gate_nn = gate_nn
+        _reset(self.gate_nn)
+
+    def forward(self, x, batch, size: int):
+        gate = self.gate_nn(x).view(-1, 1)
+        top = torch.full((size, 1), float("-inf"), dtype=gate.dtype, device=gate.device)
+        top = top.scatter_reduce(0, batch.view(-1, 1), gate.detach(), reduce="amax", include_self=True)
+        e = torch.exp(gate - top.index_select(0, batch))
+        denom = torch.zeros((size, 1), dtype=gate.dtype, device=gate.device).index_add_(0, batch, e)
+        alpha = e / (denom.index_select(0, batch) + 1e-16)
+        return torch.zeros((size, x.size(-1)), dtype=x.dtype, device=x.device).index_add_(0, batch, alpha * x)
+
+
+def _drum_split(graph):
+    """(perm, n_drum): node ids with drum nodes first (original order kept), sized without a host sync when
+    the graph came from the device builder."""
+    cached = getattr(graph, "_drum_split", None)
+    if cached is not None:
+        return cached
+    is_drum = graph.is_drum
+    n_drum = getattr(graph, "n_drum", None)
+    if n_drum is None:
+        n_drum = int(is_drum.sum())
+    perm = torch.argsort(is_drum.to(torch.uint8), descending=True, stable=True)
+    graph._drum_split = (perm, int(n_drum))
+    return graph._drum_split
+
+
+class ContentEncoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        d = self.d
+        self.dropout_layer = nn.Dropout(p=self.dropout)
+        self.non_drums_pitch_emb = nn.Linear(N_PITCH_TOKENS, d // 2)
+        self.drums_pitch_emb = nn.Linear(N_PITCH_TOKENS, d // 2)
+        self.dur_emb = nn.Linear(N_DUR_TOKENS, d // 2)
+        self.bn_non_drums = nn.BatchNorm1d(num_features=d // 2)
+        self.bn_drums = nn.BatchNorm1d(num_features=d // 2)
+        self.bn_dur = nn.BatchNorm1d(num_features=d // 2)
+        self.chord_encoder = nn.Linear(d * (MAX_SIMU_TOKENS - 1), d)
+        self.graph_encoder = GCN(dropout=self.dropout, input_dim=d, hidden_dim=d, n_layers=self.gnn_n_layers,
+                                 num_relations=N_EDGE_TYPES, batch_norm=self.batch_norm)
+        gate_nn = nn.Sequential(MLP(input_dim=d, output_dim=1, num_layers=1, activation=False, dropout=self.dropout),
+                                nn.BatchNorm1d(1))
+        self.graph_attention = GlobalAttention(gate_nn)
+        self.bars_encoder = nn.Linear(self.n_bars * d, d)
+
+    def _embed(self, tokens, pitch_emb, pitch_bn):
+        """tokens [k, 15, 230] one-hot -> chord embedding [k, d] (model.py:355-388)."""
+        k, t, half = tokens.size(0), tokens.size(1), self.d // 2
+        pitch = pitch_bn(pitch_emb(tokens[..., :N_PITCH_TOKENS]).view(-1, half)).view(k, t, half)
+        dur = self.bn_dur(self.dur_emb(tokens[..., N_PITCH_TOKENS:]).view(-1, half)).view(k, t, half)
+        chord = self.chord_encoder(torch.cat((pitch, dur), dim=-1).view(k, t * self.d))
+        return self.dropout_layer(F.relu(chord))
+
+    def forward(self, graph):
+        c = graph.c_tensor[:, 1:, :]                         # drop SOS
+        perm, n_drum = _drum_split(graph)
+        drums = self._embed(c.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
+        others = self._embed(c.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
+        x = torch.empty((c.size(0), self.d), dtype=drums.dtype, device=drums.device)
+        x = x.index_copy(0, perm, torch.cat((drums, others), dim=0))
+        graph.x = x.float()
+        graph.distinct_bars = graph.bars + self.n_bars * graph.batch
+        h = self.graph_encoder(graph)
+        n_seg = _n_segments(graph, self.n_bars)
+        with torch.autocast(device_type=h.device.type, enabled=False):
+            pooled = self.graph_attention(h.float(), batch=graph.distinct_bars, size=n_seg)
+        return self.bars_encoder(pooled.view(-1, self.n_bars * self.d))
+
+
+def _n_segments(graph, n_bars: int) -> int:
+    n_graphs = getattr(graph, "num_graphs", None)
+    if n_graphs is None:
+        n_graphs = int(graph.batch[-1]) + 1
+    return int(n_graphs) * n_bars
+
+
+class StructureEncoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        self.cnn_encoder = CNNEncoder(dense_dim=self.d, output_dim=self.d, dropout=self.dropout,
+                                      batch_norm=self.batch_norm)
+        self.bars_encoder = nn.Linear(self.n_bars * self.d, self.d)
+
+    def forward(self, graph):
+        bars = graph.s_tensor.view(-1, N_TRACKS, self.resolution * 4)
+        return self.bars_encoder(self.cnn_encoder(bars).view(-1, self.n_bars * self.d))
+
+
+class Encoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        self.s_encoder = StructureEncoder(**kwargs)
+        self.c_encoder = ContentEncoder(**kwargs)
+        self.dropout_layer = nn.Dropout(p=self.dropout)
+        self.linear_merge = nn.Linear(2 * self.d, self.d)
+        self.bn_linear_merge = nn.BatchNorm1d(num_features=self.d)
+        self.linear_mu = nn.Linear(self.d, self.d)
+        self.linear_log_var = nn.Linear(self.d, self.d)
+
+    def forward(self, graph):
+        z_s = self.s_encoder(graph)
+        z_c = self.c_encoder(graph)
+        z = self.dropout_layer(torch.cat((z_c, z_s), dim=1))
+        z = self.dropout_layer(F.relu(self.bn_linear_merge(self.linear_merge(z))))
+        return self.linear_mu(z), self.linear_log_var(z)
+
+
+class StructureDecoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        self.bars_decoder = nn.Linear(self.d, self.d * self.n_bars)
+        self.cnn_decoder = CNNDecoder(input_dim=self.d, dense_dim=self.d, dropout=self.dropout,
+                                      batch_norm=self.batch_norm)
+
+    def forward(self, z_s):
+        out = self.cnn_decoder(self.bars_decoder(z_s).reshape(-1, self.d))
+        return out.view(z_s.size(0), self.n_bars, N_TRACKS, -1)
+
+
+class ContentDecoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        d = self.d
+        self.bars_decoder = nn.Linear(d, d * self.n_bars)
+        self.graph_decoder = GCN(dropout=self.dropout, input_dim=d, hidden_dim=d, n_layers=self.gnn_n_layers,
+                                 num_relations=N_EDGE_TYPES, batch_norm=self.batch_norm)
+        self.chord_decoder = nn.Linear(d, d * (MAX_SIMU_TOKENS - 1))
+        self.drums_pitch_emb = nn.Linear(d // 2, N_PITCH_TOKENS)
+        self.non_drums_pitch_emb = nn.Linear(d // 2, N_PITCH_TOKENS)
+        self.dur_emb = nn.Linear(d // 2, N_DUR_TOKENS)
+        self.dropout_layer = nn.Dropout(p=self.dropout)
+
+    def forward(self, z_c, s):
+        d, half = self.d, self.d // 2
+        z_bar = self.bars_decoder(z_c).view(-1, d)                  # one row per (sequence, bar)
+        s.distinct_bars = s.bars + self.n_bars * s.batch
+        s.x = z_bar.index_select(0, s.distinct_bars).float()        # every node starts from its bar's code
+        h = self.graph_decoder(s)
+        h = self.dropout_layer(self.chord_decoder(h).view(-1, MAX_SIMU_TOKENS - 1, d))
+        # both pitch heads on every node, then select per node: no compaction, no host sync
+        is_drum = s.is_drum.view(-1, 1, 1)
+        pitch = torch.where(is_drum, self.drums_pitch_emb(h[..., :half]), self.non_drums_pitch_emb(h[..., :half]))
+        return torch.cat((pitch, self.dur_emb(h[..., half:])), dim=-1)
+
+
+class Decoder(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.__dict__.update(kwargs)
+        self.lin_decoder = nn.Linear(self.d, 2 * self.d)
+        self.batch_norm = nn.BatchNorm1d(num_features=2 * self.d)
+        self.dropout = nn.Dropout(p=self.dropout)
+        self.s_decoder = StructureDecoder(**kwargs)
+        self.c_decoder = ContentDecoder(**kwargs)
+        self.sigmoid_thresh = 0.5
+
+    def _structure_from_binary(self, s_tensor) -> Graph:
+        """bool [B, n_bars, 4, 32] -> batched graph on the model's device (model.py:596-607)."""
+        return graphs_from_tensor(s_tensor, device=next(self.parameters()).device)
+
+    def _binary_from_logits(self, s_logits):
+        s = torch.sigmoid(s_logits) >= self.sigmoid_thresh
+        empty = ~s.flatten(-2).any(dim=-1)
+        s[..., 0, 0] |= empty                                      # fake activation (model.py:617-621)
+        return s
+
+    def _structure_from_logits(self, s_logits) -> Graph:
+        return self._structure_from_binary(self._binary_from_logits(s_logits))
+
+    def forward(self, z, s=None):
+        z = self.dropout(F.relu(self.batch_norm(self.lin_decoder(z))))
+        z_s, z_c = z[:, : self.d], z[:, self.d:]
+        s_logits = self.s_decoder(z_s)
+        if s is None:
+            s = self._structure_from_logits(s_logits.detach())
+        return s_logits, self.c_decoder(z_c, s)
+
+
+class VAE(nn.Module):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.encoder = Encoder(**kwargs)
+        self.decoder = Decoder(**kwargs)
+
+    def forward(self, graph, noise: Optional[torch.Tensor] = None):
+        mu, log_var = self.encoder(graph)
+        eps = torch.randn_like(mu) if noise is None else noise
+        z = torch.exp(0.5 * log_var) * eps + mu
+        return self.decoder(z, graph), mu, log_var
