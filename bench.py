@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — LMD16 VAE training step (graph build + fwd + loss + bwd + gradient all-reduce + Adam).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--precision bf16|fp32] [--impl reference]
+
+Contract (see the task statement): prints ONE JSON line. `value` = sequences/s with the step's inputs (bool
+structure tensor + int16 note tokens) already resident in HBM; `e2e` = the same step fed from pinned HOST
+buffers through the public API (H2D copies and a D2H read of the loss inside the timed region); `roofline` =
+the dominant kernel of the message-passing path timed live with CUDA events over the timed region;
+`cpu_baseline` = the oracle port (oracle/model_oracle.py) on this box's host cores, bounded sample.
+For N > 1 launch with torchrun (one rank per GPU, NCCL); batch per GPU is fixed (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+MODEL_CFG = dict(dropout=0, batch_norm=True, gnn_n_layers=8, d=512, n_bars=16, resolution=8)  # training.json + n_bars=16
+ADAM = dict(lr=5e-6, betas=(0.9, 0.98), eps=1e-9)                                             # training.json optimizer
+DENSITY = 0.25
+WORKLOAD = "LMD16 VAE train step (16 bars x 4 tracks x 32 steps), synthetic Bernoulli(0.25) pianorolls, random init"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p["bf16_tflops_sustained"], source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(gpu_index)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.split(",") for r in open(self.file.name).read().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.file.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any("Active" in r[5 + i] and "Not" not in r[5 + i] for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_oracle_step_factory(batch: int, n_bars: int, seed: int = 0):
+    """One fwd + loss + bwd of the oracle port (reference algorithm, plain PyTorch CPU) on a bounded sample."""
+    from oracle import graph_oracle as go
+    from oracle import model_oracle as mo
+    import polyphemus_b200 as pb
+
+    cfg = dict(MODEL_CFG, n_bars=n_bars)
+    torch.manual_seed(0)
+    sd0 = pb.VAE(**cfg, device=torch.device("cpu")).state_dict()   # parameter container only (random init)
+    sd = mo.leaf_state(sd0)
+    s_np = go.synthetic_structure(batch, n_bars, DENSITY, seed)
+
+    def step():
+        arrays = go.batch_graph(s_np)                               # graph construction is part of the step
+        tokens = mo.synthetic_tokens(arrays.num_nodes, seed)
+        gb = mo.make_batch(arrays, tokens)
+        ctx = mo.Ctx(training=True)
+        (s_logits, c_logits), mu, log_var = mo.vae(sd, gb, n_bars, cfg["d"], ctx)
+        loss, _ = mo.losses(gb.s_tensor, s_logits, gb.c_tensor, c_logits, mu, log_var)
+        for v in sd.values():
+            if v.grad is not None:
+                v.grad = None
+        loss.backward()
+        return float(loss)
+
+    return step
+
+
+def time_cpu_baseline(batch: int, n_bars: int, steps: int, warmup: int):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_oracle_step_factory(batch, n_bars)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    return batch / min(times), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = args.cpu_batch
+    t_all = time.perf_counter()
+    value, times = time_cpu_baseline(batch, MODEL_CFG["n_bars"], max(1, args.steps), max(0, min(args.warmup, 1)))
+    ms = 1e3 * statistics.mean(times)
+    sample = (f"oracle port (reference algorithm, PyTorch CPU fp32) of the LMD16 step on batch {batch} "
+              f"(graph build + fwd + loss + bwd), best of {len(times)}")
+    line = {
+        "impl": "reference", "metric": "LMD16 train seqs/s", "value": value, "unit": "seq/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": batch, "n_bars": 16, "d": 512, "gnn_n_layers": 8},
+        "cpu_baseline": {"value": value, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ roofline
+def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: str, pk: dict, p_drop: float):
+    """Per-kernel-family algorithmic bytes / flops per launch and achieved rates."""
+    r = 6
+    k = (r + 1) * d
+    s = 2 if precision == "bf16" else 8        # bytes per GEMM-operand element (bf16, or TF32 hi+lo fp32 pair)
+    s_da = 2 if precision == "bf16" else 4
+    eb = 8 if p_drop > 0 else 4
+    parts = 444 * 32 * d * 4
+    algo = {
+        "pb_agg_fwd": ("hbm", n * d * 4 + eb * e + 4 * (n * r + 1) + 128 * d + n * k * s),
+        "pb_agg_bwd": ("hbm", n * k * s_da + 2 * n * d * 4 + 16 * e + 4 * (n + 1) + n * d * 4 + 128 * d + parts),
+        "pb_bn_stats": ("hbm", n * d * 4),
+        "pb_bn_relu_res_fwd": ("hbm", 3 * n * d * 4),
+        "pb_bn_relu_res_bwd": ("hbm", 4 * n * d * 4 + n * d * s),
+        "pb_rgcn_gemm_fwd": ("tensor", 2 * n * k * d),
+        "pb_rgcn_gemm_bwd_data": ("tensor", 2 * n * k * d),
+        "pb_rgcn_gemm_bwd_weight": ("tensor", 2 * n * k * d),
+    }
+    mma_passes = 1 if precision == "bf16" else 3
+    rows = []
+    for name, (bound, work) in algo.items():
+        if name not in summary:
+            continue
+        ent = summary[name]
+        avg_s = ent["ms"] / ent["calls"] * 1e-3
+        if bound == "hbm":
+            achieved, peak, unit = work / avg_s / 1e9, pk["hbm"], "GB/s"
+        else:
+            achieved, peak, unit = work / avg_s / 1e12, pk["tf_sustained"], "TFLOP/s"
+        rows.append({"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                     "frac": achieved / peak, "avg_ms": avg_s * 1e3, "launches_per_step": ent["calls"] / steps,
+                     "ms_per_step": ent["ms"] / steps, "algorithmic_per_launch": work,
+                     **({"executed_mma_passes": mma_passes} if bound == "tensor" else {})})
+    rows.sort(key=lambda x: -x["ms_per_step"])
+    return rows
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU (training.json batch_size)")
+    ap.add_argument("--precision", choices=["bf16", "fp32"], default="bf16")
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (sequences)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gcl-dropout", type=float, default=0.1, help="GCL message dropout (hard-wired 0.1 in the reference)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    import polyphemus_b200 as pb
+    from polyphemus_b200 import _ffi
+    from polyphemus_b200.train import TrainStep, device_batch, synthetic_host_batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: polyphemus_b200 has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    pb.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = pb.VAE(**MODEL_CFG, device=dev).to(dev).train()
+    for m in model.modules():
+        if isinstance(m, pb.GCL):
+            m.dropout = args.gcl_dropout
+    step_fn = TrainStep(model, autocast_bf16=args.precision == "bf16", **ADAM)
+
+    # a few distinct batches so the step cannot specialise on one graph; each rank gets its own shard
+    n_variants = 2
+    hosts = [synthetic_host_batch(args.batch, MODEL_CFG["n_bars"], DENSITY, seed=1000 * rank + i) for i in range(n_variants)]
+    resident = [(h.s_tensor.to(dev), h.tokens.to(dev)) for h in hosts]
+
+    def step_resident(i):
+        s_dev, tok = resident[i % n_variants]
+        from polyphemus_b200.train import HostBatch
+        graph = device_batch(HostBatch(s_dev.clone(), tok), dev)
+        return step_fn(graph)
+
+    def step_e2e(i):
+        graph = device_batch(hosts[i % n_variants], dev)            # pinned host -> device inside the timed region
+        loss, _ = step_fn(graph)
+        return float(loss)                                          # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM; per-kernel CUDA events recorded live
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    _ffi.profiler.reset()
+    _ffi.profiler.enabled = True
+    launches0 = _ffi.launch_counter["n"]
+    total_ms = timed(step_resident, args.steps)
+    launches = _ffi.launch_counter["n"] - launches0
+    _ffi.profiler.enabled = False
+    summary = _ffi.profiler.summary()
+    # ---- timed region 2: end to end from pinned host memory
+    e2e_ms = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    n_nodes = sum(h.tokens.size(0) for h in hosts) / n_variants
+    graph0 = device_batch(hosts[0], dev)
+    n_edges = graph0.num_edges
+    global_batch = args.batch * world
+    value = global_batch * args.steps / (total_ms * 1e-3)
+    e2e_value = global_batch * args.steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        rows = kernel_table(summary, int(n_nodes), int(n_edges), MODEL_CFG["d"], args.steps, args.precision, pk,
+                            args.gcl_dropout)
+        ours_ms = sum(v["ms"] for v in summary.values()) / args.steps
+        top = rows[0] if rows else None
+        hbm_rows = [r for r in rows if r["bound"] == "hbm"]
+        hbm_bytes = sum(r["algorithmic_per_launch"] * r["launches_per_step"] for r in hbm_rows)
+        hbm_ms = sum(r["ms_per_step"] for r in hbm_rows)
+        roofline = None
+        if top:
+            roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+                        "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": pk["source"],
+                        "share_of_step": top["ms_per_step"] / (total_ms / args.steps)}
+        cpu = None
+        if not args.no_cpu_baseline:
+            v, times = time_cpu_baseline(args.cpu_batch, MODEL_CFG["n_bars"], 2, 1)
+            cpu = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"oracle port (reference algorithm, PyTorch CPU fp32), LMD16 batch {args.cpu_batch}: graph build + "
+                             f"fwd + loss + bwd, best of {len(times)} after 1 warm-up ({min(times):.2f} s/step)"}
+        line = {
+            "metric": "LMD16 train seqs/s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32 (tf32x3 tensor-core split)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": args.batch, "global_batch": global_batch, "n_bars": 16, "d": 512,
+                       "gnn_n_layers": 8, "nodes_per_gpu": int(n_nodes), "edges_per_gpu": int(n_edges),
+                       "gcl_dropout": args.gcl_dropout, "parallelism": f"dp{world}",
+                       "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
+                       "step": "device graph build + fwd + loss + bwd + NCCL grad all-reduce + Adam"},
+            "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": hosts[0].nbytes, "d2h_bytes_per_step": 4 + 32},
+            "gpu_launches": launches, "roofline": roofline,
+            "mp_layer_hbm": {"achieved": hbm_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None, "peak": pk["hbm"],
+                             "unit": "GB/s", "frac": hbm_bytes / (hbm_ms * 1e-3) / 1e9 / pk["hbm"] if hbm_ms else None,
+                             "note": "all HBM-bound message-passing kernels (aggregate fwd/bwd, BN/ReLU/residual fwd/bwd)"},
+            "kernels": rows, "our_kernels_ms_per_step": ours_ms, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

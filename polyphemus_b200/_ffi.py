@@ -89,6 +89,57 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+# ---------------------------------------------------------------------------------------------------------
+# Launch accounting + optional per-call CUDA-event timing (bench.py's roofline measurement). Every entry into
+# the library goes through `call`, so `launch_counter` is the number of OUR kernels launched (memsets and
+# host-only queries are not counted).
+LAUNCHES = {
+    "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 10,
+    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 1, "pb_dropout_mask": 1,
+    "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_rgcn_gemm_bwd_weight": 2,
+    "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
+    "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,
+}
+launch_counter = {"n": 0}
+
+
+class EventProfiler:
+    """Brackets every library call with CUDA events on the launching stream; resolved after a synchronize."""
+
+    def __init__(self):
+        self.records = []       # (name, start_event, end_event, meta)
+        self.enabled = False
+
+    def reset(self):
+        self.records = []
+
+    def summary(self):
+        """{name: {"calls": n, "ms": total_ms, "meta": last meta}} — call after torch.cuda.synchronize()."""
+        out = {}
+        for name, e0, e1, meta in self.records:
+            ent = out.setdefault(name, {"calls": 0, "ms": 0.0, "meta": meta})
+            ent["calls"] += 1
+            ent["ms"] += e0.elapsed_time(e1)
+        return out
+
+
+profiler = EventProfiler()
+
+
+def call(name: str, *args, meta=None) -> None:
+    fn = getattr(lib(), name)
+    if profiler.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        profiler.records.append((name, e0, e1, meta))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+    launch_counter["n"] += LAUNCHES.get(name, 1)
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = lib().pb_last_error()

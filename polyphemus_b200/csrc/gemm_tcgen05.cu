@@ -160,6 +160,10 @@ struct Cfg {
   static constexpr int kStageBytes = kSplit * (kABytes + kBBytes);
   static constexpr int kStages = BF16 ? 4 : 3;
   static constexpr int kTmemCols = 2 * BN;
+  // The tensor core adds each MMA into the fp32 accumulator with truncation, so a long K chain drifts by
+  // ~2^-24 per MMA (measured: 1e-4 at K=3584 with three TF32 passes). The fp32-grade mode therefore hands the
+  // accumulator to the CUDA cores every kPromoteKBlocks k-blocks (round-to-nearest adds in registers).
+  static constexpr int kPromoteKBlocks = BF16 ? (1 << 30) : 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -245,11 +249,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         const int split = t / tiles_mn;
         const int kb0 = split * p.k_blocks_per_split;
         const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
-        mbar_wait(tmem_empty + buf, buf_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + buf * C::BN;
-        uint32_t accum = 0;
+        uint32_t d_tmem = 0, accum = 0;
+        int in_chunk = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (in_chunk == 0) {  // start (a chunk of) an accumulation in a free TMEM buffer
+            mbar_wait(tmem_empty + buf, buf_phase ^ 1);
+            tc_fence_after();
+            d_tmem = tmem_base + buf * C::BN;
+            accum = 0;
+          }
           mbar_wait(full + stage, phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * C::kStageBytes);
@@ -269,10 +277,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
           }
           umma_commit(empty + stage);  // smem stage reusable once these MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++in_chunk == C::kPromoteKBlocks || kb == kb1 - 1) {
+            umma_commit(tmem_full + buf);  // (partial) accumulator complete
+            buf ^= 1;
+            if (buf == 0) buf_phase ^= 1;
+            in_chunk = 0;
+          }
         }
-        umma_commit(tmem_full + buf);  // accumulator complete
-        buf ^= 1;
-        if (buf == 0) buf_phase ^= 1;
       }
     }
   } else {
@@ -280,52 +291,84 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int buf = 0;
     uint32_t buf_phase = 0;
+    // one 32-column chunk of one output row: bias / convert / store
+    auto store32 = [&](const float* v, int64_t row, int col, int split) {
+      if (p.out_bf16) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)split * p.split_stride +
+                           (size_t)row * p.ldd + col;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 q;
+          q.x = pack_bf16x2(v[j + 0], v[j + 1]);
+          q.y = pack_bf16x2(v[j + 2], v[j + 3]);
+          q.z = pack_bf16x2(v[j + 4], v[j + 5]);
+          q.w = pack_bf16x2(v[j + 6], v[j + 7]);
+          *reinterpret_cast<uint4*>(o + j) = q;
+        }
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)row * p.ldd + col;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 q = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.bias) {
+            const float4 b = ldg4(p.bias + col + j);
+            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
+          }
+          *reinterpret_cast<float4*>(o + j) = q;
+        }
+      }
+    };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int split = t / tiles_mn, mn = t - split * tiles_mn;
       const int64_t m0 = (int64_t)(mn / p.num_n_tiles) * C::BM;
       const int n0 = (mn % p.num_n_tiles) * C::BN;
-      mbar_wait(tmem_full + buf, buf_phase);
-      tc_fence_after();
+      const int kb0 = split * p.k_blocks_per_split;
+      const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
       const int64_t row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.m;
+      const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+      if constexpr (BF16) {
+        // single accumulation: stream TMEM -> registers -> global
+        mbar_wait(tmem_full + buf, buf_phase);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < C::BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * C::BN + c0), v);
-        const int col = n0 + c0;
-        if (row_ok && col < p.n) {   // n is a multiple of 32 (host check): whole 32-column chunk in range
-          if (p.out_bf16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)split * p.split_stride +
-                               (size_t)row * p.ldd + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 q;
-              q.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-              q.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-              q.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-              q.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-              *reinterpret_cast<uint4*>(o + j) = q;
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)row * p.ldd + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 q = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                     __uint_as_float(v[j + 3]));
-              if (p.bias) {
-                const float4 b = ldg4(p.bias + col + j);
-                q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
-              }
-              *reinterpret_cast<float4*>(o + j) = q;
-            }
-          }
+        for (int c0 = 0; c0 < C::BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(buf * C::BN + c0), v);
+          if (row_ok && n0 + c0 < p.n)   // n is a multiple of 32 (host check): whole chunk in range
+            store32(reinterpret_cast<const float*>(v), row, n0 + c0, split);
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + buf);
+        buf ^= 1;
+        if (buf == 0) buf_phase ^= 1;
+      } else {
+        // promoted accumulation: add every TMEM chunk into fp32 registers (round-to-nearest)
+        float acc[C::BN];
+#pragma unroll
+        for (int j = 0; j < C::BN; ++j) acc[j] = 0.f;
+        const int n_chunks = (kb1 - kb0 + C::kPromoteKBlocks - 1) / C::kPromoteKBlocks;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          mbar_wait(tmem_full + buf, buf_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int c0 = 0; c0 < C::BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(lane_base + (uint32_t)(buf * C::BN + c0), v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[c0 + j] += __uint_as_float(v[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + buf);
+          buf ^= 1;
+          if (buf == 0) buf_phase ^= 1;
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < C::BN; c0 += 32)
+          if (row_ok && n0 + c0 < p.n) store32(acc + c0, row, n0 + c0, split);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + buf);
-      buf ^= 1;
-      if (buf == 0) buf_phase ^= 1;
     }
   }
 
@@ -349,6 +392,46 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int n_split
     }
     reinterpret_cast<float4*>(out)[i] = s;
   }
+}
+
+// dst[c][r] = src[r][c]  (fp32, 32x32 tiles through padded smem). Only the PB_F32 weight-gradient path uses
+// it: tcgen05 kind::tf32 with MN-major operands needs a different shared-memory atom than the 16-byte-swizzled
+// tiles used here, so that mode contracts over K-major transposed copies instead.
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, int64_t rows, int64_t cols,
+                                                           int64_t ld_src, float* __restrict__ dst, int64_t ld_dst) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t r = r0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int64_t c = c0 + ty + i, r = r0 + tx;
+    if (c < cols && r < rows) dst[(size_t)c * ld_dst + r] = tile[tx][ty + i];
+  }
+}
+
+static int transpose_f32(const float* src, int64_t rows, int64_t cols, int64_t ld_src, float* dst, int64_t ld_dst,
+                         cudaStream_t st) {
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  PB_REQUIRE(grid.y <= 65535u * 32u, "transpose: too many rows");
+  if (grid.y > 65535u) {  // fold very tall matrices over several launches
+    const int64_t step = (int64_t)65535 * 32;
+    for (int64_t r = 0; r < rows; r += step) {
+      const int64_t nr = std::min(step, rows - r);
+      dim3 g((unsigned)((cols + 31) / 32), (unsigned)((nr + 31) / 32));
+      transpose_f32_kernel<<<g, 256, 0, st>>>(src + (size_t)r * ld_src, nr, cols, ld_src, dst + r, ld_dst);
+      PB_LAUNCH_CHECK();
+    }
+    return PB_OK;
+  }
+  transpose_f32_kernel<<<grid, 256, 0, st>>>(src, rows, cols, ld_src, dst, ld_dst);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
 }
 
 // ------------------------------------------------------------------------------------------- host side
@@ -507,10 +590,15 @@ extern "C" int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t
   return rc < 0 ? rc : PB_OK;
 }
 
+static inline int64_t pad4(int64_t v) { return (v + 3) / 4 * 4; }
+
 extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k) {
   if (m <= 0 || d <= 0 || k <= 0) return 0;
   const int s = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false));
-  return align_up((size_t)s * k * d * sizeof(float), 256);
+  const size_t partials = align_up((size_t)s * k * d * sizeof(float), 256);
+  const size_t transposed = 2 * (align_up((size_t)k * pad4(m) * sizeof(float), 256) +
+                                 align_up((size_t)d * pad4(m) * sizeof(float), 256));   // PB_F32 only
+  return partials + transposed;
 }
 
 extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
@@ -524,13 +612,30 @@ extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64
   PB_REQUIRE(workspace_bytes >= pb_rgcn_gemm_bwd_weight_workspace_bytes(m, d, k), "pb_rgcn_gemm_bwd_weight: workspace too small");
   const bool bf16 = dtype == PB_BF16;
   const int splits = bwd_weight_splits(m, d, k, bf16);
-  Operand a{a_hi, a_lo, m, k, lda, true};   // stored [nodes, K]: output rows (K) contiguous -> MN-major
-  Operand b{g_hi, g_lo, m, d, ldg, true};   // stored [nodes, d]
   cudaStream_t st = as_stream(stream);
   float* part = reinterpret_cast<float*>(workspace);
   const int64_t n_elems = (int64_t)k * d;
-  rc = bf16 ? launch_gemm<true>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st)
-            : launch_gemm<false>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+  if (bf16) {
+    Operand a{a_hi, a_lo, m, k, lda, true};   // stored [nodes, K]: output rows (K) contiguous -> MN-major
+    Operand b{g_hi, g_lo, m, d, ldg, true};   // stored [nodes, d]
+    rc = launch_gemm<true>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+  } else {
+    // K-major transposed copies: At [K, m], gt [d, m]
+    const int64_t mp = pad4(m);
+    const int s_max = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false));
+    char* wsp = reinterpret_cast<char*>(workspace) + align_up((size_t)s_max * k * d * sizeof(float), 256);
+    float* at_hi = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)k * mp * sizeof(float), 256);
+    float* at_lo = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)k * mp * sizeof(float), 256);
+    float* gt_hi = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)d * mp * sizeof(float), 256);
+    float* gt_lo = reinterpret_cast<float*>(wsp);
+    if ((rc = transpose_f32(reinterpret_cast<const float*>(a_hi), m, k, lda, at_hi, mp, st))) return rc;
+    if ((rc = transpose_f32(reinterpret_cast<const float*>(a_lo), m, k, lda, at_lo, mp, st))) return rc;
+    if ((rc = transpose_f32(reinterpret_cast<const float*>(g_hi), m, d, ldg, gt_hi, mp, st))) return rc;
+    if ((rc = transpose_f32(reinterpret_cast<const float*>(g_lo), m, d, ldg, gt_lo, mp, st))) return rc;
+    Operand a{at_hi, at_lo, k, m, mp, false};
+    Operand b{gt_hi, gt_lo, d, m, mp, false};
+    rc = launch_gemm<false>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+  }
   if (rc < 0) return rc;
   const int used = rc;
   const unsigned grid = (unsigned)std::min<int64_t>((n_elems / 4 + 255) / 256, (int64_t)sm_count() * 8);

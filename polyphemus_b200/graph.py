@@ -45,10 +45,9 @@ class CsrPlan:
         ws_bytes = lib.pb_csr_workspace_bytes(n, e, r)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _ffi.check(lib.pb_csr_build(edge_index.data_ptr(), edge_type.data_ptr(), edge_dist.data_ptr(), n, e, r,
-                                        self.in_ptr.data_ptr(), self.in_edge.data_ptr(), self.in_eid.data_ptr(),
-                                        self.out_ptr.data_ptr(), self.out_rec.data_ptr(), ws.data_ptr(), ws_bytes,
-                                        _ffi.stream()), "pb_csr_build")
+            _ffi.call("pb_csr_build", edge_index.data_ptr(), edge_type.data_ptr(), edge_dist.data_ptr(), n, e, r,
+                      self.in_ptr.data_ptr(), self.in_edge.data_ptr(), self.in_eid.data_ptr(),
+                      self.out_ptr.data_ptr(), self.out_rec.data_ptr(), ws.data_ptr(), ws_bytes, _ffi.stream())
         self.device = dev
         self.struct = _ffi.CsrStruct(n, e, r, 0, self.in_ptr.data_ptr(), self.in_edge.data_ptr(),
                                      self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr())
@@ -73,8 +72,8 @@ class Graph:
             e = self.edge_type.numel()
             out = torch.empty((e, N_TIMESTEPS + 1), dtype=torch.float32, device=self.edge_type.device)
             with torch.cuda.device(out.device):
-                _ffi.check(_ffi.lib().pb_edge_attrs_encode(self.edge_type.data_ptr(), self.edge_dist.data_ptr(), e,
-                                                           out.data_ptr(), _ffi.stream()), "pb_edge_attrs_encode")
+                _ffi.call("pb_edge_attrs_encode", self.edge_type.data_ptr(), self.edge_dist.data_ptr(), e,
+                          out.data_ptr(), _ffi.stream())
             self._edge_attrs = out
         return self._edge_attrs
 
@@ -144,9 +143,8 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
         totals = torch.empty(4, dtype=torch.int64, device=dev)
         ws_bytes = lib.pb_graph_workspace_bytes(total_bars)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _ffi.check(lib.pb_graph_count(s_u8.data_ptr(), total_bars, bar_bits.data_ptr(), node_ptr.data_ptr(),
-                                      edge_ptr.data_ptr(), totals.data_ptr(), ws.data_ptr(), ws_bytes, st),
-                   "pb_graph_count")
+        _ffi.call("pb_graph_count", s_u8.data_ptr(), total_bars, bar_bits.data_ptr(), node_ptr.data_ptr(),
+                  edge_ptr.data_ptr(), totals.data_ptr(), ws.data_ptr(), ws_bytes, st)
         n, e, n_drum, _ = (int(v) for v in totals.tolist())          # the one host sync
         edge_index = torch.empty((2, e), dtype=torch.int64, device=dev)
         edge_type = torch.empty(e, dtype=torch.uint8, device=dev)
@@ -157,10 +155,10 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
         bars = torch.empty(n, dtype=torch.int64, device=dev)
         batch = torch.empty(n, dtype=torch.int64, device=dev)
         node_track = torch.empty(n, dtype=torch.uint8, device=dev)
-        _ffi.check(lib.pb_graph_fill(bar_bits.data_ptr(), node_ptr.data_ptr(), edge_ptr.data_ptr(), total_bars, n_bars,
-                                     edge_index.data_ptr(), e, edge_type.data_ptr(), edge_dist.data_ptr(),
-                                     _ffi.ptr(edge_attrs), node_features.data_ptr(), is_drum.data_ptr(),
-                                     bars.data_ptr(), batch.data_ptr(), node_track.data_ptr(), st), "pb_graph_fill")
+        _ffi.call("pb_graph_fill", bar_bits.data_ptr(), node_ptr.data_ptr(), edge_ptr.data_ptr(), total_bars, n_bars,
+                  edge_index.data_ptr(), e, edge_type.data_ptr(), edge_dist.data_ptr(), _ffi.ptr(edge_attrs),
+                  node_features.data_ptr(), is_drum.data_ptr(), bars.data_ptr(), batch.data_ptr(),
+                  node_track.data_ptr(), st)
     if write_back is not None:
         write_back.copy_(s_u8.view(write_back.dtype).reshape(write_back.shape))
     g = Graph(edge_index=edge_index, edge_type=edge_type, edge_dist=edge_dist, node_features=node_features,
@@ -216,7 +214,6 @@ def decode_edge_attrs(edge_type: torch.Tensor, edge_attr: torch.Tensor):
     d_out = torch.empty(e, dtype=torch.uint8, device=dev)
     if e:
         with torch.cuda.device(dev):
-            _ffi.check(_ffi.lib().pb_edge_attrs_decode(edge_type.data_ptr(), edge_type.stride(0), edge_attr.data_ptr(),
-                                                       edge_attr.stride(0), e, t_out.data_ptr(), d_out.data_ptr(),
-                                                       _ffi.stream()), "pb_edge_attrs_decode")
+            _ffi.call("pb_edge_attrs_decode", edge_type.data_ptr(), edge_type.stride(0), edge_attr.data_ptr(),
+                      edge_attr.stride(0), e, t_out.data_ptr(), d_out.data_ptr(), _ffi.stream())
     return t_out, d_out

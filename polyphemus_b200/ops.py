@@ -32,15 +32,7 @@ _PRECISIONS = {"fp32": _ffi.PB_F32, "bf16": _ffi.PB_BF16}
 _default_precision = "fp32"
 _seed_counter = itertools.count()
 
-# every C-ABI kernel launch is counted so that bench.py can report `gpu_launches` from the product itself
-launch_counter = {"n": 0}
-
-# kernel launches per ABI call (see csrc/*.cu); used only for the counter above
-_LAUNCHES = {
-    "pb_edge_table_fwd": 1, "pb_agg_fwd": 1, "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_bn_stats": 2,
-    "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1, "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,
-    "pb_rgcn_gemm_bwd_weight": 2, "pb_rgcn_gemm_bwd_data": 1, "pb_agg_bwd": 1, "pb_edge_table_bwd": 1,
-}
+launch_counter = _ffi.launch_counter
 
 
 def set_precision(name: str) -> None:
@@ -56,8 +48,7 @@ def get_precision() -> str:
 
 
 def _call(name: str, *args) -> None:
-    _ffi.check(getattr(_ffi.lib(), name)(*args), name)
-    launch_counter["n"] += _LAUNCHES.get(name, 1)
+    _ffi.call(name, *args)
 
 
 def next_seed() -> int:

@@ -1,0 +1,211 @@
+"""Training-step plumbing around the hot path: losses, synthetic LMD-shaped batches, data-parallel step.
+
+* ``vae_losses``     — same arithmetic as ``PolyphemusTrainer._losses`` (training.py:298-347), including its
+                       quirks (the structure term is computed from ``s_tensor`` itself, training.py:307; the KLD
+                       weight is the trainer's ``beta``, 0 as shipped, training.py:116), but returns tensors
+                       instead of calling ``.item()`` seven times per step.
+* ``synthetic_host_batch`` / ``device_batch`` — Bernoulli(p) structures and random note tokens in the on-disk
+                       layout of the reference dataset (bool ``s_tensor``, int16 token ids, preprocess.py:210),
+                       expanded on the device to the ``c_tensor`` one-hot layout of data.py:234-259.
+* ``GradAllReducer`` — data-parallel gradient exchange: one flat fp32 buffer holds every ``.grad``; buckets are
+                       all-reduced with NCCL as soon as backward has produced them.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .graph import Graph, graphs_from_tensor
+from .vae import MAX_SIMU_TOKENS, N_DUR_TOKENS, N_PITCH_TOKENS
+
+PITCH_SOS, PITCH_EOS, PITCH_PAD = 128, 129, 130
+DUR_SOS, DUR_EOS, DUR_PAD = 96, 97, 98
+
+
+def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float = 0.0, c_tokens=None):
+    """Total loss and its parts (tensors). ``c_tokens`` int [N,16,2], when given, replaces the argmax over
+    the one-hot ``c_tensor`` (same targets, no N x 15 x 230 read)."""
+    logits = c_logits.reshape(-1, c_logits.size(-1)).float()
+    if c_tokens is not None:
+        tgt = c_tokens[:, 1:, :].reshape(-1, 2).long()
+        pitch_true, dur_true = tgt[:, 0], tgt[:, 1]
+    else:
+        tgt = c_tensor[..., 1:, :].reshape(-1, c_tensor.size(-1))
+        pitch_true = tgt[:, :N_PITCH_TOKENS].argmax(dim=1)
+        dur_true = tgt[:, N_PITCH_TOKENS:].argmax(dim=1)
+    # training.py:307 overwrites the structure logits with the structure tensor itself
+    s_as_logits = s_tensor.reshape(-1, *s_logits.shape[2:]).float()
+    s_loss = F.binary_cross_entropy_with_logits(s_as_logits.reshape(-1), s_tensor.reshape(-1).float())
+    pitch_loss = F.cross_entropy(logits[:, :N_PITCH_TOKENS], pitch_true, ignore_index=PITCH_PAD)
+    dur_loss = F.cross_entropy(logits[:, N_PITCH_TOKENS:], dur_true, ignore_index=DUR_PAD)
+    kld = (-0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp(), dim=1)).mean()
+    total = pitch_loss + dur_loss + s_loss + beta * kld
+    return total, {"pitch": pitch_loss, "dur": dur_loss, "structure": s_loss, "kld": kld}
+
+
+# ------------------------------------------------------------------------------------------ synthetic data
+@dataclass
+class HostBatch:
+    """What a data loader would hand over: pinned host memory in the dataset's compact layout."""
+    s_tensor: torch.Tensor      # bool  [B, n_bars, 4, 32]
+    tokens: torch.Tensor        # int16 [N, 16, 2]  (pitch id, duration id) for every active (bar, track, t)
+
+    @property
+    def nbytes(self) -> int:
+        return self.s_tensor.numel() * self.s_tensor.element_size() + self.tokens.numel() * self.tokens.element_size()
+
+
+def synthetic_tokens(num_nodes: int, generator: torch.Generator) -> torch.Tensor:
+    """[N,16,2] token ids: SOS, k~U{1..14} notes, EOS, PAD... (constants.py:22-41, preprocess.py)."""
+    k = torch.randint(1, 15, (num_nodes, 1), generator=generator)
+    pos = torch.arange(MAX_SIMU_TOKENS).unsqueeze(0)
+    pitch = torch.randint(0, 128, (num_nodes, MAX_SIMU_TOKENS), generator=generator)
+    dur = torch.randint(0, 96, (num_nodes, MAX_SIMU_TOKENS), generator=generator)
+    note, eos = (pos >= 1) & (pos <= k), pos == k + 1
+    pitch = torch.where(note, pitch, torch.full_like(pitch, PITCH_PAD))
+    dur = torch.where(note, dur, torch.full_like(dur, DUR_PAD))
+    pitch = torch.where(eos, torch.full_like(pitch, PITCH_EOS), pitch)
+    dur = torch.where(eos, torch.full_like(dur, DUR_EOS), dur)
+    pitch[:, 0], dur[:, 0] = PITCH_SOS, DUR_SOS
+    return torch.stack((pitch, dur), dim=-1).to(torch.int16)
+
+
+def synthetic_host_batch(batch: int, n_bars: int, p: float = 0.25, seed: int = 0, pin: bool = True) -> HostBatch:
+    rng = np.random.default_rng(seed)
+    s = rng.random((batch, n_bars, 4, 32)) < p
+    empty = ~s.reshape(batch, n_bars, -1).any(axis=-1)
+    s[empty, 0, 0] = True                       # the dataset applies data.py:152-153 before filtering c_tensor
+    n = int(s.sum())
+    tokens = synthetic_tokens(n, torch.Generator().manual_seed(seed))
+    s_t = torch.from_numpy(s)
+    if pin and torch.cuda.is_available():
+        s_t, tokens = s_t.pin_memory(), tokens.pin_memory()
+    return HostBatch(s_t, tokens)
+
+
+def onehot_content(tokens: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+    """int [N,16,2] -> float [N,16,230] one-hot pitch | duration (data.py:234-259), on the tokens' device."""
+    n, t = tokens.shape[:2]
+    out = torch.zeros((n, t, N_PITCH_TOKENS + N_DUR_TOKENS), dtype=dtype, device=tokens.device)
+    idx = tokens.long()
+    out.scatter_(2, idx[..., :1], 1.0)
+    out.scatter_(2, idx[..., 1:] + N_PITCH_TOKENS, 1.0)
+    return out
+
+
+def device_batch(host: HostBatch, device, onehot_dtype=torch.float32) -> Graph:
+    """Host batch -> device graph with ``s_tensor`` / ``c_tensor`` / ``c_tokens`` attached (H2D copies +
+    device graph build + device one-hot expansion)."""
+    s_dev = host.s_tensor.to(device, non_blocking=True)
+    tok_dev = host.tokens.to(device, non_blocking=True)
+    graph = graphs_from_tensor(s_dev)
+    if graph.num_nodes != tok_dev.size(0):
+        raise ValueError(f"{tok_dev.size(0)} token rows for {graph.num_nodes} nodes")
+    graph.s_tensor = s_dev.view(-1, 4, 32).float()
+    graph.c_tokens = tok_dev
+    graph.c_tensor = onehot_content(tok_dev, onehot_dtype)
+    return graph
+
+
+# ------------------------------------------------------------------------------------------ data parallel
+class GradAllReducer:
+    """Flat-buffer gradient all-reduce (sum then 1/world) overlapped with backward.
+
+    Every parameter's ``.grad`` is a view into one contiguous fp32 buffer. Parameters are bucketed in reverse
+    registration order (the order backward produces them); a post-accumulate hook counts ready parameters and
+    launches ``all_reduce`` on a bucket the moment it is complete. Parameters that never receive a gradient
+    (the 12 ``decoder.s_decoder.*`` tensors, whose loss term is constant — training.py:307) keep a zero slot,
+    identically on every rank, and their buckets are flushed by ``finish()``.
+    """
+
+    def __init__(self, params, bucket_mb: float = 32.0, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buckets = []            # (start, end, n_params)
+        self._bucket_of = {}
+        order = list(reversed(self.params))
+        limit = int(bucket_mb * (1 << 20) / 4)
+        off, start, count = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[p] = len(self.buckets)
+            off += n
+            count += 1
+            if off - start >= limit:
+                self.buckets.append((start, off, count))
+                start, count = off, 0
+        if count:
+            self.buckets.append((start, off, count))
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+
+    def _launch(self, b: int) -> None:
+        if self._launched[b]:
+            return
+        self._launched[b] = True
+        s, e, _ = self.buckets[b]
+        self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def _hook(self, p) -> None:
+        b = self._bucket_of[p]
+        self._ready[b] += 1
+        if self._ready[b] == self.buckets[b][2]:
+            self._launch(b)
+
+    def zero_grad(self) -> None:
+        self.flat.zero_()
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+
+    def finish(self) -> None:
+        """Flush incomplete buckets, wait for all reductions, average."""
+        if self.world == 1:
+            return
+        for b in range(len(self.buckets)):
+            self._launch(b)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
+        self.flat.mul_(1.0 / self.world)
+
+
+class TrainStep:
+    """graph build -> forward -> loss -> backward -> gradient all-reduce -> Adam (train.py:176-207 config)."""
+
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.98), eps: float = 1e-9, autocast_bf16: bool = False,
+                 beta_kld: float = 0.0, bucket_mb: float = 32.0):
+        self.model = model
+        self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb)
+        self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, fused=model_is_cuda(model))
+        self.autocast_bf16 = autocast_bf16
+        self.beta_kld = beta_kld
+
+    def __call__(self, graph: Graph, noise: Optional[torch.Tensor] = None):
+        self.reducer.zero_grad()
+        dev_type = next(self.model.parameters()).device.type
+        with torch.autocast(device_type=dev_type, dtype=torch.bfloat16, enabled=self.autocast_bf16):
+            (s_logits, c_logits), mu, log_var = self.model(graph, noise=noise)
+            loss, parts = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_logits, mu, log_var,
+                                     beta=self.beta_kld, c_tokens=getattr(graph, "c_tokens", None))
+        loss.backward()
+        self.reducer.finish()
+        self.opt.step()
+        return loss.detach(), parts
+
+
+def model_is_cuda(model) -> bool:
+    return next(model.parameters()).is_cuda

@@ -1,0 +1,192 @@
+"""CPU tier for the product's host side: C-ABI surface, closed-form graph plan logic (host-compiled),
+state-dict / seeded-init contract, loss restatement, data-parallel reducer over gloo (world size 2)."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, ROOT, golden
+from oracle import graph_oracle as go
+from oracle import model_oracle as mo
+
+
+def test_abi_library_exports_every_declared_symbol(built_lib):
+    header = open(os.path.join(ROOT, "include", "polyphemus_b200.h")).read()
+    declared = set(re.findall(r"\b(pb_[a-z0-9_]+)\s*\(", header))
+    lib = ctypes.CDLL(built_lib)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/polyphemus_b200.h but not exported"
+    from polyphemus_b200 import _ffi
+
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    lib.pb_version.restype = ctypes.c_int
+    assert lib.pb_version() == 100
+
+
+def test_kernels_are_native_blackwell(built_lib):
+    """SASS evidence (B200_PROFILING.md): tcgen05.mma -> UTC*MMA, TMA -> UTMALDG, tcgen05.ld -> LDTM."""
+    sass = subprocess.run(["cuobjdump", "-sass", built_lib], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+    assert "HMMA." not in sass.replace("UTCHMMA", "")          # no legacy mma.sync path
+
+
+def test_no_cpu_fallback():
+    import polyphemus_b200 as pb
+
+    with pytest.raises((pb.PolyphemusB200Error, RuntimeError)):
+        s = torch.zeros(1, 2, 4, 32, dtype=torch.bool)
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present; the no-device path cannot be exercised")
+        pb.graphs_from_tensor(s)
+    layer = pb.GCL(64, 64, 6, torch.nn.Linear(32, 64))
+    with pytest.raises((pb.PolyphemusB200Error, RuntimeError)):
+        layer(torch.randn(3, 64), torch.zeros(2, 1, dtype=torch.long), torch.zeros(1), torch.zeros(1, 32))
+
+
+@pytest.fixture(scope="module")
+def host_plan_lib(tmp_path_factory):
+    out = tmp_path_factory.mktemp("host") / "libgraph_plan_host.so"
+    src = os.path.join(ROOT, "tests", "host", "graph_plan_host.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", str(out), src], check=True)
+    return ctypes.CDLL(str(out))
+
+
+def _host_edges(lib, bar):
+    bits = np.array([sum(int(bar[k, t]) << t for t in range(32)) for k in range(4)], dtype=np.uint32)
+    out = np.zeros((1100, 4), dtype=np.int64)
+    cnt = np.zeros(5, dtype=np.int32)
+    n = lib.pbh_bar_edges(bits.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p),
+                          cnt.ctypes.data_as(ctypes.c_void_p))
+    return out[:n], cnt
+
+
+def test_graph_plan_logic_matches_oracle(host_plan_lib):
+    """The integer code the CUDA builder runs per (bar, timestep) (csrc/graph_plan.h), compiled for the host."""
+    rng = np.random.default_rng(0)
+    bars = [rng.random((4, 32)) < p for p in (0.01, 0.03, 0.1, 0.25, 0.5, 0.8, 1.0) for _ in range(150)]
+    ref = golden("graph_random.npz")
+    bars += list(ref["edge.s_out"].reshape(-1, 4, 32))
+    for bar in bars:
+        bar = bar.copy()
+        if not bar.any():
+            bar[0, 0] = True
+        want, n = go.bar_edges(bar)
+        got, cnt = _host_edges(host_plan_lib, bar)
+        assert cnt[0] == n and cnt[4] == want.shape[0]
+        np.testing.assert_array_equal(got, want)
+
+
+def test_state_dict_contract_and_seeded_init():
+    import polyphemus_b200 as pb
+
+    gold = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))
+    torch.manual_seed(0)
+    vae = pb.VAE(**gold["config"], device=torch.device("cpu"))
+    sd = vae.state_dict()
+    assert list(sd.keys()) == list(gold["keys"].keys())
+    assert {k: list(v.shape) for k, v in sd.items()} == gold["keys"]
+    assert sum(p.numel() for p in vae.parameters()) == gold["n_params"] == 42210909
+    lmd16 = pb.VAE(**{**gold["config"], "n_bars": 16}, device=torch.device("cpu"))
+    assert sum(p.numel() for p in lmd16.parameters()) == 56905309
+    # the edge network is one module shared by all layers of a GCN (model.py:175)
+    enc = vae.encoder.c_encoder.graph_encoder
+    assert all(layer.nn is enc.layers[0].nn for layer in enc.layers)
+
+
+def test_seeded_init_equals_golden_parameters():
+    import polyphemus_b200 as pb
+
+    ref = golden("vae_step.npz")
+    cfg = json.loads(str(ref["config"]))
+    torch.manual_seed(3)                                   # make_golden.py seeds the reference VAE with 3
+    vae = pb.VAE(**cfg, device=torch.device("cpu"))
+    sd = vae.state_dict()
+    for k in ("encoder.c_encoder.graph_encoder.layers.1.weight", "decoder.c_decoder.graph_decoder.layers.0.root",
+              "encoder.c_encoder.graph_encoder.layers.0.nn.weight", "decoder.c_decoder.chord_decoder.weight"):
+        assert torch.equal(sd[k], torch.from_numpy(ref["sd." + k])), k
+
+
+def test_loss_restatement_matches_oracle():
+    from polyphemus_b200.train import onehot_content, synthetic_tokens, vae_losses
+
+    g = torch.Generator().manual_seed(0)
+    n, b = 37, 3
+    tokens = synthetic_tokens(n, g)
+    c_tensor = onehot_content(tokens)
+    torch.testing.assert_close(c_tensor, mo.onehot_content(tokens.long()))
+    c_logits = torch.randn(n, 15, 230, generator=g)
+    s_tensor = (torch.rand(b * 2, 4, 32, generator=g) < 0.25).float()
+    s_logits = torch.randn(b, 2, 4, 32, generator=g)
+    mu, log_var = torch.randn(b, 8, generator=g), torch.randn(b, 8, generator=g)
+    want, wp = mo.losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta=0.3)
+    for toks in (None, tokens):
+        got, gp = vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta=0.3, c_tokens=toks)
+        torch.testing.assert_close(got, want)
+        for k in wp:
+            torch.testing.assert_close(gp[k], wp[k])
+
+
+def test_philox_host_matches_known_answer():
+    """Philox4x32-10 known-answer test (Random123 kat vectors): counter 0 / key 0 and all-ones."""
+    def philox(c, k):
+        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+        c, k = list(c), list(k)
+        for _ in range(10):
+            p0, p1 = M0 * c[0], M1 * c[2]
+            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+        return c
+    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    assert philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+DP_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from polyphemus_b200.train import GradAllReducer
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+unused = model[3]                      # never used in forward: grad stays None (cf. s_decoder, training.py:307)
+red = GradAllReducer(model.parameters(), bucket_mb=0.0001)
+data = torch.randn(world * 6, 8, generator=torch.Generator().manual_seed(1))
+target = torch.randn(world * 6, 4, generator=torch.Generator().manual_seed(2))
+for step in range(2):
+    red.zero_grad()
+    shard = slice(rank * 6, (rank + 1) * 6)
+    loss = ((model[2](model[1](model[0](data[shard]))) - target[shard]) ** 2).mean()
+    loss.backward()
+    red.finish()
+# single-process reference: average of per-shard gradients
+ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
+ref.load_state_dict(model.state_dict())
+grads = None
+for r in range(world):
+    ref.zero_grad()
+    shard = slice(r * 6, (r + 1) * 6)
+    ((ref[2](ref[1](ref[0](data[shard]))) - target[shard]) ** 2).mean().backward()
+    g = [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in ref.parameters()]
+    grads = g if grads is None else [a + b for a, b in zip(grads, g)]
+for p, g in zip(model.parameters(), grads):
+    assert torch.allclose(p.grad, g / world, atol=1e-6), (rank, p.shape)
+assert float(unused.weight.grad.abs().max()) == 0.0
+assert len(red.buckets) > 1
+print("rank", rank, "ok")
+"""
+
+
+def test_grad_all_reducer_world_size_2_gloo(tmp_path):
+    script = tmp_path / "dp_check.py"
+    script.write_text(DP_SCRIPT)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", str(script), ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2

@@ -1,0 +1,327 @@
+"""Per-kernel GPU parity through the C ABI: tcgen05 GEMMs, aggregation fwd/bwd, BatchNorm fwd/bwd.
+
+Checker = oracle.model_oracle (CPU, fp64/fp32) and exact fp64 matmuls of the operands; tolerances:
+  PB_F32 mode  rtol 1e-4 / atol 1e-5  (BASELINE.json north_star)
+  PB_BF16 mode compared against fp64 arithmetic on the *bf16-rounded operands* at rtol 2e-3 (accumulation
+  only), and against the fp32 oracle at the bf16 budget rtol 3e-2 / atol 3e-2 of the output scale.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import model_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = dict(rtol=1e-4, atol=1e-5)
+
+
+def _ffi():
+    from polyphemus_b200 import _ffi
+
+    return _ffi
+
+
+def tf32_split(t):
+    hi = (t.contiguous().view(torch.int32) & -8192).view(torch.float32)   # 0xFFFFE000
+    return hi, t - hi
+
+
+def operands(t, dtype):
+    ffi = _ffi()
+    if dtype == ffi.PB_BF16:
+        return t.to(torch.bfloat16).contiguous(), None
+    hi, lo = tf32_split(t)
+    return hi.contiguous(), lo.contiguous()
+
+
+def as_f64(hi, lo):
+    return hi.double() if lo is None else hi.double() + lo.double()
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------- GEMMs
+@pytest.mark.parametrize("dtype_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("m,d", [(128, 64), (300, 128), (1000, 512), (4133, 256)])
+def test_gemm_fwd(cuda, dtype_name, m, d):
+    ffi = _ffi()
+    dtype = ffi.PB_BF16 if dtype_name == "bf16" else ffi.PB_F32
+    k = 7 * d
+    g = torch.Generator(device="cpu").manual_seed(m + d)
+    a = torch.randn(m, k, generator=g).to(cuda)
+    wt = (torch.randn(d, k, generator=g) / np.sqrt(k)).to(cuda)
+    bias = torch.randn(d, generator=g).to(cuda)
+    a_hi, a_lo = operands(a, dtype)
+    w_hi, w_lo = operands(wt, dtype)
+    out = torch.full((m, d), float("nan"), device=cuda)
+    ffi.check(ffi.lib().pb_rgcn_gemm_fwd(ptr(a_hi), ptr(a_lo), k, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), d, m, d, k,
+                                         dtype, st()), "pb_rgcn_gemm_fwd")
+    torch.cuda.synchronize()
+    ref = as_f64(a_hi, a_lo) @ as_f64(w_hi, w_lo).t() + bias.double()
+    tol = dict(rtol=2e-3, atol=2e-3) if dtype_name == "bf16" else F32_TOL
+    torch.testing.assert_close(out.double(), ref, **tol)
+    # cross-check with the on-device fp32 CUDA-core contraction
+    chk = torch.empty_like(out)
+    a32, w32 = as_f64(a_hi, a_lo).float().contiguous(), as_f64(w_hi, w_lo).float().contiguous()   # keep alive
+    ffi.check(ffi.lib().pb_gemm_f32_check(ptr(a32), k, ptr(w32), k, ptr(bias), ptr(chk), d, m, d, k, 0, 1, st()),
+              "pb_gemm_f32_check")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, chk, rtol=2e-3 if dtype_name == "bf16" else 1e-4, atol=2e-3 if dtype_name == "bf16" else 1e-5)
+
+
+@pytest.mark.parametrize("dtype_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("m,d", [(128, 64), (777, 128), (2000, 512)])
+def test_gemm_bwd_data(cuda, dtype_name, m, d):
+    ffi = _ffi()
+    dtype = ffi.PB_BF16 if dtype_name == "bf16" else ffi.PB_F32
+    k = 7 * d
+    gen = torch.Generator(device="cpu").manual_seed(7 * m + d)
+    g = torch.randn(m, d, generator=gen).to(cuda)
+    w = (torch.randn(k, d, generator=gen) / np.sqrt(d)).to(cuda)
+    g_hi, g_lo = operands(g, dtype)
+    w_hi, w_lo = operands(w, dtype)
+    d_a = torch.empty((m, k), dtype=torch.bfloat16 if dtype == ffi.PB_BF16 else torch.float32, device=cuda)
+    ffi.check(ffi.lib().pb_rgcn_gemm_bwd_data(ptr(g_hi), ptr(g_lo), d, ptr(w_hi), ptr(w_lo), ptr(d_a), k, m, d, k, dtype,
+                                              st()), "pb_rgcn_gemm_bwd_data")
+    ref = as_f64(g_hi, g_lo) @ as_f64(w_hi, w_lo).t()
+    tol = dict(rtol=1e-2, atol=1e-2) if dtype_name == "bf16" else F32_TOL   # bf16 output rounding
+    torch.testing.assert_close(d_a.double(), ref, **tol)
+
+
+@pytest.mark.parametrize("dtype_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("m,d", [(100, 64), (5000, 128), (20000, 512)])
+def test_gemm_bwd_weight(cuda, dtype_name, m, d):
+    ffi = _ffi()
+    dtype = ffi.PB_BF16 if dtype_name == "bf16" else ffi.PB_F32
+    k = 7 * d
+    gen = torch.Generator(device="cpu").manual_seed(3 * m + d)
+    a = torch.randn(m, k, generator=gen).to(cuda)
+    g = (torch.randn(m, d, generator=gen) / np.sqrt(m)).to(cuda)
+    a_hi, a_lo = operands(a, dtype)
+    g_hi, g_lo = operands(g, dtype)
+    ws_bytes = ffi.lib().pb_rgcn_gemm_bwd_weight_workspace_bytes(m, d, k)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    d_w = torch.full((k, d), float("nan"), device=cuda)
+    ffi.check(ffi.lib().pb_rgcn_gemm_bwd_weight(ptr(a_hi), ptr(a_lo), k, ptr(g_hi), ptr(g_lo), d, ptr(d_w), m, d, k,
+                                                dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
+    ref = as_f64(a_hi, a_lo).t() @ as_f64(g_hi, g_lo)
+    tol = dict(rtol=2e-3, atol=2e-3) if dtype_name == "bf16" else F32_TOL
+    torch.testing.assert_close(d_w.double(), ref, **tol)
+    # determinism of the split-K reduction
+    d_w2 = torch.empty_like(d_w)
+    ffi.check(ffi.lib().pb_rgcn_gemm_bwd_weight(ptr(a_hi), ptr(a_lo), k, ptr(g_hi), ptr(g_lo), d, ptr(d_w2), m, d, k,
+                                                dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
+    assert torch.equal(d_w, d_w2)
+
+
+def test_weight_prep(cuda):
+    ffi = _ffi()
+    r, d = 6, 128
+    w = torch.randn(r, d, d, device=cuda)
+    root = torch.randn(d, d, device=cuda)
+    wcat = torch.cat((w.view(r * d, d), root), 0)
+    k = (r + 1) * d
+    w_bf, wt_bf = torch.empty((k, d), dtype=torch.bfloat16, device=cuda), torch.empty((d, k), dtype=torch.bfloat16, device=cuda)
+    ffi.check(ffi.lib().pb_weight_prep(ptr(w), ptr(root), r, d, ffi.PB_BF16, ptr(w_bf), None, ptr(wt_bf), None, st()), "prep")
+    assert torch.equal(w_bf, wcat.to(torch.bfloat16)) and torch.equal(wt_bf, wcat.t().to(torch.bfloat16))
+    bufs = [torch.empty((k, d), device=cuda), torch.empty((k, d), device=cuda), torch.empty((d, k), device=cuda),
+            torch.empty((d, k), device=cuda)]
+    ffi.check(ffi.lib().pb_weight_prep(ptr(w), ptr(root), r, d, ffi.PB_F32, *[ptr(b) for b in bufs], st()), "prep")
+    hi, lo = tf32_split(wcat)
+    assert torch.equal(bufs[0], hi) and torch.equal(bufs[1], lo)
+    assert torch.equal(bufs[2], hi.t()) and torch.equal(bufs[3], lo.t())
+    assert torch.equal(bufs[0] + bufs[1], wcat)
+
+
+# ------------------------------------------------------------------------------------------------- aggregation
+def _graph(cuda, bsz=6, n_bars=3, p=0.3, seed=1):
+    import polyphemus_b200 as pb
+
+    s_np = go.synthetic_structure(bsz, n_bars, p, seed)
+    arrays = go.batch_graph(s_np)
+    g = pb.graphs_from_tensor(torch.from_numpy(s_np).to(cuda))
+    return g, arrays
+
+
+def _oracle_h(x, arrays, table, keep=None, p=0.0):
+    """H[v, r, :] = mean over segment of relu(x[src]*T[dist]) (float64 on CPU)."""
+    n, d = x.shape
+    ei = torch.from_numpy(arrays.edge_index)
+    et, ed = torch.from_numpy(arrays.edge_type), torch.from_numpy(arrays.edge_dist)
+    msg = torch.relu(x[ei[0]] * table[ed])
+    if keep is not None:
+        msg = msg * keep.to(msg.dtype) / (1 - p)
+    h = torch.zeros(n * 6, d, dtype=x.dtype).index_add_(0, ei[1] * 6 + et, msg)
+    cnt = torch.zeros(n * 6, dtype=x.dtype).index_add_(0, ei[1] * 6 + et, torch.ones(ei.shape[1], dtype=x.dtype))
+    return (h / cnt.clamp(min=1).unsqueeze(1)).view(n, 6 * d)
+
+
+@pytest.mark.parametrize("d", [64, 256, 512])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_agg_fwd(cuda, d, p_drop):
+    ffi = _ffi()
+    from polyphemus_b200 import ops
+
+    g, arrays = _graph(cuda)
+    n, k = g.num_nodes, 7 * d
+    gen = torch.Generator().manual_seed(d)
+    x = torch.randn(n, d, generator=gen)
+    nn_w, nn_b = torch.randn(d, 32, generator=gen) * 0.3, torch.randn(d, generator=gen) * 0.3
+    table = torch.empty(32, d, device=cuda)
+    ffi.check(ffi.lib().pb_edge_table_fwd(ptr(nn_w.to(cuda)), ptr(nn_b.to(cuda)), d, ptr(table), st()), "table")
+    torch.testing.assert_close(table.cpu(), nn_w.t() + nn_b, rtol=0, atol=0)
+    seed = 1234567
+    keep = ops.dropout_keep_mask(arrays.edge_index.shape[1], d, p_drop, seed, cuda).cpu() if p_drop else None
+    if p_drop:
+        assert abs(keep.float().mean().item() - (1 - p_drop)) < 0.01
+    ref = torch.cat((_oracle_h(x.double(), arrays, table.cpu().double(), keep, p_drop), x.double()), 1)
+    xd = x.to(cuda)
+    a_hi, a_lo = torch.empty(n, k, device=cuda), torch.empty(n, k, device=cuda)
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_hi), ptr(a_lo), k, ffi.PB_F32, p_drop, seed,
+                                   st()), "agg_fwd")
+    torch.testing.assert_close((a_hi.double() + a_lo.double()).cpu(), ref, rtol=1e-6, atol=1e-6)
+    assert ((a_hi.view(torch.int32) & 8191) == 0).all()          # hi is a clean TF32 value
+    a_bf = torch.empty(n, k, dtype=torch.bfloat16, device=cuda)
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_bf), None, k, ffi.PB_BF16, p_drop, seed,
+                                   st()), "agg_fwd")
+    torch.testing.assert_close(a_bf.float().cpu(), ref.float(), rtol=8e-3, atol=1e-6)
+    # bit-reproducible
+    a2 = torch.empty_like(a_hi)
+    l2 = torch.empty_like(a_lo)
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a2), ptr(l2), k, ffi.PB_F32, p_drop, seed,
+                                   st()), "agg_fwd")
+    assert torch.equal(a2, a_hi) and torch.equal(l2, a_lo)
+
+
+@pytest.mark.parametrize("d", [64, 256, 512, 1024])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_agg_bwd(cuda, d, p_drop):
+    ffi = _ffi()
+    from polyphemus_b200 import ops
+
+    g, arrays = _graph(cuda, bsz=5, n_bars=2, p=0.35, seed=d)
+    n, k = g.num_nodes, 7 * d
+    gen = torch.Generator().manual_seed(d + 1)
+    x = torch.randn(n, d, generator=gen, dtype=torch.float64).float().double().requires_grad_(True)
+    table = (torch.randn(32, d, generator=gen, dtype=torch.float64) * 0.5).float().double().requires_grad_(True)
+    d_a = torch.randn(n, k, generator=gen, dtype=torch.float64).float().double()
+    gy = torch.randn(n, d, generator=gen, dtype=torch.float64).float().double()
+    seed = 42
+    keep = ops.dropout_keep_mask(arrays.edge_index.shape[1], d, p_drop, seed, cuda).cpu() if p_drop else None
+    a_ref = torch.cat((_oracle_h(x, arrays, table, keep, p_drop), x), 1)
+    (a_ref * d_a).sum().backward()
+    gx_ref = x.grad + gy
+    n_part = ffi.lib().pb_agg_bwd_num_partials()
+    x_dev, t_dev, gy_dev = x.detach().float().to(cuda), table.detach().float().to(cuda), gy.float().to(cuda)
+    for dtype, tol in ((ffi.PB_F32, dict(rtol=1e-5, atol=1e-5)), (ffi.PB_BF16, dict(rtol=2e-2, atol=2e-2))):
+        da_dev = d_a.float().to(cuda) if dtype == ffi.PB_F32 else d_a.to(torch.bfloat16).to(cuda)
+        gx = torch.empty(n, d, device=cuda)
+        parts = torch.empty(n_part, 32, d, device=cuda)
+        ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gx),
+                                       ptr(parts), p_drop, seed, st()), "agg_bwd")
+        torch.testing.assert_close(gx.double().cpu(), gx_ref, **tol)
+        g_w, g_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+        ffi.check(ffi.lib().pb_edge_table_bwd(ptr(parts), n_part, d, ptr(g_w), ptr(g_b), st()), "table_bwd")
+        scale = float(table.grad.abs().max())
+        torch.testing.assert_close(g_w.double().cpu(), table.grad.t(), rtol=tol["rtol"], atol=tol["atol"] * max(1.0, scale))
+        torch.testing.assert_close(g_b.double().cpu(), table.grad.sum(0), rtol=tol["rtol"], atol=tol["atol"] * 8 * max(1.0, scale))
+        if dtype == ffi.PB_F32:
+            gx2, parts2 = torch.empty_like(gx), torch.empty_like(parts)
+            ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev),
+                                           ptr(gx2), ptr(parts2), p_drop, seed, st()), "agg_bwd")
+            assert torch.equal(gx, gx2) and torch.equal(parts, parts2)
+
+
+# ------------------------------------------------------------------------------------------------- BatchNorm
+@pytest.mark.parametrize("m,d", [(37, 64), (4000, 512), (70001, 256)])
+def test_bn_relu_res_fwd_bwd(cuda, m, d):
+    ffi = _ffi()
+    lib = ffi.lib()
+    gen = torch.Generator().manual_seed(m)
+    out = (torch.randn(m, d, generator=gen) * 2 + 50.0)         # large mean: the variance must not cancel
+    x = torch.randn(m, d, generator=gen)
+    gamma, beta = torch.rand(d, generator=gen) + 0.5, torch.randn(d, generator=gen)
+    rm, rv = torch.randn(d, generator=gen), torch.rand(d, generator=gen) + 0.5
+    gy = torch.randn(m, d, generator=gen)
+    # fp64 reference of the forward through torch (training-mode batch statistics)
+    rm64, rv64 = rm.double().clone(), rv.double().clone()
+    y_ref = x.double() + torch.relu(torch.nn.functional.batch_norm(out.double(), rm64, rv64, gamma.double(), beta.double(),
+                                                                   True, 0.1, 1e-5))
+    dev = lambda t: t.to(cuda).contiguous()
+    out_d, x_d, gamma_d, beta_d, rm_d, rv_d, gy_d = map(dev, (out, x, gamma, beta, rm, rv, gy))
+    ws_bytes = lib.pb_bn_workspace_bytes(m, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    coef, save = torch.empty(3, d, device=cuda), torch.empty(2, d, device=cuda)
+    ffi.check(lib.pb_bn_stats(ptr(out_d), d, m, d, ptr(gamma_d), ptr(beta_d), 1e-5, 0.1, ptr(rm_d), ptr(rv_d), ptr(save),
+                              ptr(coef), ptr(ws), ws_bytes, st()), "bn_stats")
+    y = torch.empty(m, d, device=cuda)
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef), ptr(y), m, d, 1, st()), "bn_fwd")
+    torch.testing.assert_close(y.double().cpu(), y_ref, rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(rm_d.double().cpu(), rm64, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(rv_d.double().cpu(), rv64, rtol=1e-4, atol=1e-5)
+    mean64, var64 = out.double().mean(0), out.double().var(0, unbiased=False)
+    torch.testing.assert_close(save[0].double().cpu(), mean64, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(save[1].double().cpu(), 1 / torch.sqrt(var64 + 1e-5), rtol=1e-5, atol=0)
+    # fp64 reference of the backward. The ReLU mask is a step function: an element whose pre-activation is
+    # within rounding of 0 may legitimately flip and then moves its whole column's reductions, so the reference
+    # takes the mask exactly as the kernel evaluates it: fma(fl32(out - mean), scale, beta) > 0.
+    mu32, sc32, be32 = coef[0].cpu(), coef[1].cpu(), coef[2].cpu()
+    ctr32 = out - mu32
+    mask = (ctr32.double() * sc32.double() + be32.double()) > 0
+    xhat = ctr32.double() * save[1].double().cpu()
+    gz = gy.double() * mask
+    g_beta_ref, g_gamma_ref = gz.sum(0), (gz * xhat).sum(0)
+    g_out_ref = sc32.double() * (gz - g_beta_ref / m - xhat * g_gamma_ref / m)
+    g_hi, g_lo = torch.empty(m, d, device=cuda), torch.empty(m, d, device=cuda)
+    g_gamma, g_beta, g_bias = (torch.empty(d, device=cuda) for _ in range(3))
+    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, ffi.PB_F32,
+                                     ptr(g_hi), ptr(g_lo), d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
+                                     st()), "bn_bwd")
+    scale = float(g_out_ref.abs().max())
+    torch.testing.assert_close((g_hi.double() + g_lo.double()).cpu(), g_out_ref, rtol=1e-4, atol=1e-5 * max(1.0, scale))
+    torch.testing.assert_close(g_gamma.double().cpu(), g_gamma_ref, rtol=1e-4, atol=1e-4 * float(g_gamma_ref.abs().max()))
+    torch.testing.assert_close(g_beta.double().cpu(), g_beta_ref, rtol=1e-4, atol=1e-4 * float(g_beta_ref.abs().max()))
+    assert g_bias.abs().max().item() < 1e-3 * max(1.0, scale) * np.sqrt(m)      # column sums of a BN gradient vanish
+    # and the formula itself against autograd on a kink-free subset of columns
+    o64 = out.double().requires_grad_(True)
+    g64 = gamma.double().requires_grad_(True)
+    z64 = torch.nn.functional.batch_norm(o64, None, None, g64, beta.double(), True, 0.1, 1e-5)
+    (x.double() + torch.relu(z64)).backward(gy.double())
+    cols = (z64.detach().abs() > 1e-3).all(dim=0)
+    if cols.any():
+        torch.testing.assert_close(g_out_ref[:, cols], o64.grad[:, cols], rtol=1e-4, atol=1e-5 * max(1.0, scale))
+    g_bf = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
+    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, ffi.PB_BF16,
+                                     ptr(g_bf), None, d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
+                                     st()), "bn_bwd")
+    torch.testing.assert_close(g_bf.double().cpu(), g_out_ref, rtol=1e-2, atol=1e-2 * max(1.0, scale))
+    # eval mode coefficients
+    coef_e = torch.empty(3, d, device=cuda)
+    ffi.check(lib.pb_bn_prepare_eval(ptr(gamma_d), ptr(beta_d), ptr(rm_d), ptr(rv_d), 1e-5, d, ptr(coef_e), st()), "bn_eval")
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef_e), ptr(y), m, d, 1, st()), "bn_fwd")
+    y_eval = x.double() + torch.relu(torch.nn.functional.batch_norm(out.double(), rm_d.double().cpu(), rv_d.double().cpu(),
+                                                                    gamma.double(), beta.double(), False, 0.1, 1e-5))
+    torch.testing.assert_close(y.double().cpu(), y_eval, rtol=1e-4, atol=2e-5)
+
+
+def test_grad_prep(cuda):
+    ffi = _ffi()
+    m, d = 3000, 128
+    g = torch.randn(m, d, device=cuda)
+    ws_bytes = ffi.lib().pb_bn_workspace_bytes(m, d)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+    hi, lo, gb = torch.empty_like(g), torch.empty_like(g), torch.empty(d, device=cuda)
+    ffi.check(ffi.lib().pb_grad_prep(ptr(g), d, m, d, ffi.PB_F32, ptr(hi), ptr(lo), d, ptr(gb), ptr(ws), ws_bytes, st()), "prep")
+    assert torch.equal(hi + lo, g)
+    torch.testing.assert_close(gb.double(), g.double().sum(0), rtol=1e-5, atol=1e-4)
+    bf = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
+    ffi.check(ffi.lib().pb_grad_prep(ptr(g), d, m, d, ffi.PB_BF16, ptr(bf), None, d, ptr(gb), ptr(ws), ws_bytes, st()), "prep")
+    assert torch.equal(bf, g.to(torch.bfloat16))
