@@ -135,17 +135,22 @@ int pb_edge_table_bwd(const float* dtable_partials, int32_t n_partials, int32_t 
  * relation (model.py:103-111):  H[v,r,:] = mean_{e in seg(v,r)} keep_e * relu(x[src_e] * T[dist_e]).
  * Writes the GEMM operand  A[v, :] = [H[v,0] | ... | H[v,R-1] | x[v]]  (row stride lda):
  *   PB_BF16: A bf16;   PB_F32: A_hi / A_lo fp32 (TF32 split, A_lo may not be NULL).
- * Dropout (model.py:133, p hard-wired 0.1 in training): keep mask from Philox4x32-10 keyed by `seed`,
- * counter (edge id, channel/4); pb_dropout_mask exposes the same mask for checking.
+ * Dropout (model.py:133, p hard-wired 0.1 in training): the keep decision of every (edge, channel) is drawn once
+ * per layer call by pb_dropout_bits — SplitMix64 hash of (seed; edge id, channel/4), four 16-bit lanes per
+ * 4-channel chunk, keep iff lane >= round(p * 65536) — packed 1 bit per channel, and read by forward, operand
+ * recompute and backward alike (keep_bits may be NULL when p_drop == 0). pb_dropout_mask exposes the same
+ * decisions as bytes [E, d] for checking.
  * Backward: gx[u] = gy_res[u] + dA[u, R*d:] + sum_{e: src=u} dH[dst_e, rel_e]/cnt * keep * 1[x*T>0] * T[dist_e]
  *           dT partials per CTA (deterministic, reduced by pb_edge_table_bwd).
  * ---------------------------------------------------------------------------------------------- */
+size_t pb_dropout_bits_bytes(int64_t n_edges, int32_t d);
+int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, void* keep_bits, pb_stream_t stream);
 int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, void* a_hi, void* a_lo,
-               int64_t lda, int32_t dtype, float p_drop, uint64_t seed, pb_stream_t stream);
+               int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, pb_stream_t stream);
 int32_t pb_agg_bwd_num_partials(void);
 int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
                int64_t ldda, int32_t dtype, const float* gy_res, float* gx, float* dtable_partials,
-               float p_drop, uint64_t seed, pb_stream_t stream);
+               const void* keep_bits, float p_drop, pb_stream_t stream);
 int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep /*[E,d]*/,
                     pb_stream_t stream);
 

@@ -60,6 +60,34 @@ __device__ __forceinline__ void column_partials(int64_t m, int d, float* __restr
 
 static inline size_t col_smem(int nv, int d) { return (size_t)nv * (kColThreads / (d / 4)) * d * sizeof(float); }
 
+// Second stage of every column reduction: block = 32 columns x kFinLanes partial-lanes. Lane py sums partials
+// py, py+kFinLanes, ... in double; the lanes are then combined in fixed order. Result in s[] of the py == 0 threads.
+constexpr int kFinLanes = 32;
+template <int NV>
+__device__ __forceinline__ bool finalize_sums(const float* __restrict__ partials, int n_part, int d, double s[NV]) {
+  __shared__ double red[NV][kFinLanes][33];
+  const int ci = threadIdx.x, py = threadIdx.y;
+  const int c = blockIdx.x * 32 + ci;
+  double acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = 0.0;
+  if (c < d)
+    for (int p = py; p < n_part; p += kFinLanes)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) acc[i] += (double)partials[((size_t)p * NV + i) * d + c];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[i][py][ci] = acc[i];
+  __syncthreads();
+  if (py != 0 || c >= d) return false;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double t = 0.0;
+    for (int l = 0; l < kFinLanes; ++l) t += red[i][l][ci];
+    s[i] = t;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------ forward stats
 __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const float* __restrict__ out, int64_t ldo,
                                                                       int64_t m, int d, float* __restrict__ partials) {
@@ -77,13 +105,10 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                          float* __restrict__ save_mean_rstd, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int p = 0; p < n_part; ++p) {
-    s1 += (double)partials[((size_t)p * 2 + 0) * d + c];
-    s2 += (double)partials[((size_t)p * 2 + 1) * d + c];
-  }
+  double s[2];
+  if (!finalize_sums<2>(partials, n_part, d, s)) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const double s1 = s[0], s2 = s[1];
   const double n = (double)m;
   const double mean = (double)out[c] + s1 / n;
   double var = (s2 - s1 * s1 / n) / n;
@@ -162,14 +187,9 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const float
 template <int NV>
 __global__ void col_finalize_kernel(const float* __restrict__ partials, int n_part, int d, float* __restrict__ o0,
                                     float* __restrict__ o1) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= d) return;
   double s[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) s[i] = 0.0;
-  for (int p = 0; p < n_part; ++p)
-#pragma unroll
-    for (int i = 0; i < NV; ++i) s[i] += (double)partials[((size_t)p * NV + i) * d + c];
+  if (!finalize_sums<NV>(partials, n_part, d, s)) return;
+  const int c = blockIdx.x * 32 + threadIdx.x;
   if (o0) o0[c] = (float)s[0];
   if (NV > 1 && o1) o1[c] = (float)s[NV > 1 ? 1 : 0];
 }
@@ -253,7 +273,7 @@ extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, 
   float* partials = reinterpret_cast<float*>(workspace);
   bn_stats_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, m, d, partials);
   PB_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, out, m, d, gamma, beta, eps, momentum,
+  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, out, m, d, gamma, beta, eps, momentum,
                                                            running_mean, running_var, save_mean_rstd, bn_coef);
   PB_LAUNCH_CHECK();
   return PB_OK;
@@ -305,7 +325,7 @@ extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo
   float* partials = reinterpret_cast<float*>(workspace);
   bn_bwd_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, m, d, partials);
   PB_LAUNCH_CHECK();
-  col_finalize_kernel<2><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_beta, g_gamma);
+  col_finalize_kernel<2><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_beta, g_gamma);
   PB_LAUNCH_CHECK();
   if (dtype == PB_BF16)
     bn_bwd_apply_kernel<true><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
@@ -315,7 +335,7 @@ extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo
                                                                          g_beta, m, d, g_hi, g_lo, ldg, partials);
   PB_LAUNCH_CHECK();
   if (g_bias) {
-    col_finalize_kernel<1><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_bias, nullptr);
+    col_finalize_kernel<1><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_bias, nullptr);
     PB_LAUNCH_CHECK();
   }
   return PB_OK;
@@ -338,7 +358,7 @@ extern "C" int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d
     grad_prep_kernel<false><<<ctas, kColThreads, col_smem(1, d), st>>>(g, ldg_in, m, d, g_hi, g_lo, ldg, partials);
   PB_LAUNCH_CHECK();
   if (g_bias) {
-    col_finalize_kernel<1><<<(d + 127) / 128, 128, 0, st>>>(partials, ctas, d, g_bias, nullptr);
+    col_finalize_kernel<1><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_bias, nullptr);
     PB_LAUNCH_CHECK();
   }
   return PB_OK;

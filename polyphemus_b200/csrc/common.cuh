@@ -72,41 +72,32 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 __device__ __forceinline__ float tf32_lo(float v, float hi) { return v - hi; }
 
-// ------------------------------------------------------------------ Philox4x32-10 (counter based, stateless)
-struct Philox {
-  static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
-  __host__ __device__ static inline void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
-    uint64_t p = (uint64_t)a * (uint64_t)b;
-    hi = (uint32_t)(p >> 32);
-    lo = (uint32_t)p;
-  }
-  // counter = (c0,c1,c2,c3), key = (k0,k1)  ->  4 x u32
-  __host__ __device__ static inline void run(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                             uint32_t k1, uint32_t out[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      uint32_t h0, l0, h1, l1;
-      mulhilo(kM0, c0, h0, l0);
-      mulhilo(kM1, c2, h1, l1);
-      uint32_t n0 = h1 ^ c1 ^ k0, n1 = l1, n2 = h0 ^ c3 ^ k1, n3 = l0;
-      c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-      k0 += kW0; k1 += kW1;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-  }
-};
-
-// keep-mask bits for channels [4*chunk, 4*chunk+4) of edge `eid`: keep iff u32 >= thresh, thresh = p * 2^32
-__host__ __device__ inline void dropout_keep4(uint64_t seed, uint32_t eid, uint32_t chunk, uint32_t thresh,
+// ------------------------------------------------------------------ counter-based dropout RNG (stateless)
+// keep-mask of GCL.message's dropout (model.py:133). One 64-bit hash per (edge, 4-channel chunk): the SplitMix64
+// output function (Stafford "Mix13" finaliser, the generator behind java.util.SplittableRandom) applied to the
+// counter seed + GOLDEN * (1 + (eid << 32 | chunk)); the four 16-bit lanes decide the four channels.
+// ~16 integer instructions per chunk — a Philox4x32-10 call costs ~5x that and made agg_fwd issue-bound.
+__host__ __device__ inline uint64_t splitmix64_mix(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline uint64_t dropout_bits(uint64_t seed, uint32_t eid, uint32_t chunk) {
+  const uint64_t ctr = ((uint64_t)eid << 32) | (uint64_t)chunk;
+  return splitmix64_mix(seed + 0x9E3779B97F4A7C15ull * (ctr + 1ull));
+}
+// keep channel i of the chunk iff its 16-bit lane >= thresh16 (= round(p * 65536))
+__host__ __device__ inline void dropout_keep4(uint64_t seed, uint32_t eid, uint32_t chunk, uint32_t thresh16,
                                               bool keep[4]) {
-  uint32_t r[4];
-  Philox::run(eid, chunk, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  const uint64_t r = dropout_bits(seed, eid, chunk);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) keep[i] = r[i] >= thresh;
+  for (int i = 0; i < 4; ++i) keep[i] = (uint32_t)((r >> (16 * i)) & 0xFFFFu) >= thresh16;
 }
 __host__ __device__ inline uint32_t dropout_thresh(float p) {
-  double t = (double)p * 4294967296.0;
-  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  double t = (double)p * 65536.0 + 0.5;
+  return t >= 65535.0 ? 65535u : (uint32_t)t;
 }
+// scale that keeps the expectation exact for the quantised probability thresh16 / 65536
+__host__ __device__ inline float dropout_scale(uint32_t thresh16) { return 65536.0f / (float)(65536u - thresh16); }
 
 }  // namespace pb

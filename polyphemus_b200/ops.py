@@ -15,6 +15,7 @@ PyTorch only owns the memory and the stream here; no arithmetic of the path runs
 from __future__ import annotations
 
 import itertools
+import os
 import threading
 from dataclasses import dataclass
 from typing import Optional
@@ -64,6 +65,7 @@ class LayerConfig:
     seed: int
     training: bool
     batch_norm: bool           # fuse BN + ReLU + residual (GCN layer) or return the raw GCL output
+    save_operand: bool = False  # keep the aggregated GEMM operand for backward instead of recomputing it
     eps: float = BN_EPS
     momentum: float = BN_MOMENTUM
 
@@ -95,6 +97,16 @@ def _weights(weight, root, r, d, dtype, st):
     return w_hi, w_lo, wt_hi, wt_lo
 
 
+def _keep_bits(n_edges: int, d: int, p: float, seed: int, dev, st: int):
+    """Packed dropout keep-bits of one layer call (None when dropout is off)."""
+    if p <= 0.0 or n_edges == 0:
+        return None
+    nbytes = _ffi.lib().pb_dropout_bits_bytes(n_edges, d)
+    bits = torch.empty(nbytes // 2, dtype=torch.int16, device=dev)
+    _call("pb_dropout_bits", n_edges, d, float(p), int(seed), bits.data_ptr(), st)
+    return bits
+
+
 class RGCLayerFn(torch.autograd.Function):
     """y = x_res + relu(BN(GCL(x)))   (cfg.batch_norm)   or   y = GCL(x)   (plain layer)."""
 
@@ -121,12 +133,15 @@ class RGCLayerFn(torch.autograd.Function):
             table = _edge_table(nn_w, nn_b, d, st)
             a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
             p = cfg.p_drop if cfg.training else 0.0
+            keep_bits = _keep_bits(plan.n_edges, d, p, cfg.seed, dev, st)
             _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
-                  cfg.dtype, p, cfg.seed, st)
+                  cfg.dtype, _ffi.ptr(keep_bits), p, st)
+            ctx.keep_bits = keep_bits
             _, _, wt_hi, wt_lo = _weights(weight, root, r, d, cfg.dtype, st)
             out = torch.empty((n, d), dtype=torch.float32, device=dev)
             _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
                   _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, cfg.dtype, st)
+            ctx.operand = (a_hi, a_lo) if cfg.save_operand else None
             if not cfg.batch_norm:
                 ctx.save_for_backward(x, weight, root, nn_w, nn_b)
                 ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
@@ -180,12 +195,15 @@ class RGCLayerFn(torch.autograd.Function):
             else:
                 _call("pb_grad_prep", gy.data_ptr(), d, n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
                       g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
-            # recompute the aggregated operand instead of keeping N x (R+1)d per layer alive
             table = _edge_table(nn_w, nn_b, d, st)
-            a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
             p = cfg.p_drop if cfg.training else 0.0
-            _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
-                  cfg.dtype, p, cfg.seed, st)
+            if ctx.operand is not None:
+                a_hi, a_lo = ctx.operand
+                ctx.operand = None
+            else:  # recompute the aggregated operand instead of keeping N x (R+1)d per layer alive
+                a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
+                _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
+                      cfg.dtype, _ffi.ptr(ctx.keep_bits), p, st)
             w_hi, w_lo, _, _ = _weights(weight, root, r, d, cfg.dtype, st)
             d_wcat = torch.empty((k, d), dtype=torch.float32, device=dev)
             wws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, d, k)
@@ -200,7 +218,8 @@ class RGCLayerFn(torch.autograd.Function):
             n_part = lib.pb_agg_bwd_num_partials()
             partials = torch.empty((n_part, _ffi.N_DISTS, d), dtype=torch.float32, device=dev)
             _call("pb_agg_bwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
-                  gy.data_ptr() if cfg.batch_norm else None, gx.data_ptr(), partials.data_ptr(), p, cfg.seed, st)
+                  gy.data_ptr() if cfg.batch_norm else None, gx.data_ptr(), partials.data_ptr(),
+                  _ffi.ptr(ctx.keep_bits), p, st)
             g_nn_w = torch.empty((d, _ffi.N_DISTS), dtype=torch.float32, device=dev)
             g_nn_b = torch.empty(d, dtype=torch.float32, device=dev)
             _call("pb_edge_table_bwd", partials.data_ptr(), n_part, d, g_nn_w.data_ptr(), g_nn_b.data_ptr(), st)
@@ -210,12 +229,24 @@ class RGCLayerFn(torch.autograd.Function):
                 None, None, None, None)
 
 
+# Operands up to this size are kept for backward (LMD16, per-GPU batch 256, bf16: 0.94 GB per layer); larger ones
+# (big batches, the fp32 hi/lo mode) are recomputed from x so that activation memory stays ~2 N d floats per layer.
+SAVE_OPERAND_MAX_BYTES = int(os.environ.get("PB200_SAVE_OPERAND_MB", "2048")) << 20
+
+
 def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, beta=None, running_mean=None,
               running_var=None, batch_norm: bool, training: bool, p_drop: float, precision: Optional[str] = None,
-              seed: Optional[int] = None, eps: float = BN_EPS, momentum: float = BN_MOMENTUM):
-    cfg = LayerConfig(dtype=_PRECISIONS[precision or _default_precision], p_drop=float(p_drop),
+              seed: Optional[int] = None, eps: float = BN_EPS, momentum: float = BN_MOMENTUM,
+              save_operand: Optional[bool] = None):
+    dtype = _PRECISIONS[precision or _default_precision]
+    if save_operand is None:
+        elem = 2 if dtype == _ffi.PB_BF16 else 8
+        save_operand = (torch.is_grad_enabled() and
+                        x.size(0) * (plan.n_relations + 1) * x.size(1) * elem <= SAVE_OPERAND_MAX_BYTES)
+    cfg = LayerConfig(dtype=dtype, p_drop=float(p_drop),
                       seed=next_seed() if seed is None else int(seed), training=bool(training),
-                      batch_norm=bool(batch_norm), eps=float(eps), momentum=float(momentum))
+                      batch_norm=bool(batch_norm), save_operand=bool(save_operand), eps=float(eps),
+                      momentum=float(momentum))
     return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg)
 
 

@@ -30,7 +30,12 @@ DUR_SOS, DUR_EOS, DUR_PAD = 96, 97, 98
 def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float = 0.0, c_tokens=None):
     """Total loss and its parts (tensors). ``c_tokens`` int [N,16,2], when given, replaces the argmax over
     the one-hot ``c_tensor`` (same targets, no N x 15 x 230 read)."""
-    logits = c_logits.reshape(-1, c_logits.size(-1)).float()
+    parts = getattr(c_logits, "_parts", None)
+    if parts is not None:
+        pitch_logits, dur_logits = (p.reshape(-1, p.size(-1)).float() for p in parts)
+    else:
+        logits = c_logits.reshape(-1, c_logits.size(-1)).float()
+        pitch_logits, dur_logits = logits[:, :N_PITCH_TOKENS], logits[:, N_PITCH_TOKENS:]
     if c_tokens is not None:
         tgt = c_tokens[:, 1:, :].reshape(-1, 2).long()
         pitch_true, dur_true = tgt[:, 0], tgt[:, 1]
@@ -41,11 +46,21 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     # training.py:307 overwrites the structure logits with the structure tensor itself
     s_as_logits = s_tensor.reshape(-1, *s_logits.shape[2:]).float()
     s_loss = F.binary_cross_entropy_with_logits(s_as_logits.reshape(-1), s_tensor.reshape(-1).float())
-    pitch_loss = F.cross_entropy(logits[:, :N_PITCH_TOKENS], pitch_true, ignore_index=PITCH_PAD)
-    dur_loss = F.cross_entropy(logits[:, N_PITCH_TOKENS:], dur_true, ignore_index=DUR_PAD)
+    pitch_loss = _masked_ce(pitch_logits, pitch_true, PITCH_PAD)
+    dur_loss = _masked_ce(dur_logits, dur_true, DUR_PAD)
     kld = (-0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp(), dim=1)).mean()
     total = pitch_loss + dur_loss + s_loss + beta * kld
     return total, {"pitch": pitch_loss, "dur": dur_loss, "structure": s_loss, "kld": kld}
+
+
+def _masked_ce(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
+    """nn.CrossEntropyLoss(ignore_index=...) (training.py:100-101): mean over the non-ignored rows of
+    logsumexp(logits) - logits[target]. Written out because the library's nll_loss reduction runs in a single
+    block and costs milliseconds on 2M rows."""
+    keep = target != ignore_index
+    picked = logits.gather(1, target.unsqueeze(1)).squeeze(1)
+    nll = torch.logsumexp(logits, dim=1) - picked
+    return (nll * keep).sum() / keep.sum()
 
 
 # ------------------------------------------------------------------------------------------ synthetic data
@@ -98,9 +113,9 @@ def onehot_content(tokens: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     return out
 
 
-def device_batch(host: HostBatch, device, onehot_dtype=torch.float32) -> Graph:
-    """Host batch -> device graph with ``s_tensor`` / ``c_tensor`` / ``c_tokens`` attached (H2D copies +
-    device graph build + device one-hot expansion)."""
+def device_batch(host: HostBatch, device, onehot: bool = False, onehot_dtype=torch.float32) -> Graph:
+    """Host batch -> device graph with ``s_tensor`` and ``c_tokens`` attached (H2D copies + device graph
+    build). ``onehot=True`` also expands the reference's ``c_tensor`` one-hot layout on the device."""
     s_dev = host.s_tensor.to(device, non_blocking=True)
     tok_dev = host.tokens.to(device, non_blocking=True)
     graph = graphs_from_tensor(s_dev)
@@ -108,7 +123,7 @@ def device_batch(host: HostBatch, device, onehot_dtype=torch.float32) -> Graph:
         raise ValueError(f"{tok_dev.size(0)} token rows for {graph.num_nodes} nodes")
     graph.s_tensor = s_dev.view(-1, 4, 32).float()
     graph.c_tokens = tok_dev
-    graph.c_tensor = onehot_content(tok_dev, onehot_dtype)
+    graph.c_tensor = onehot_content(tok_dev, onehot_dtype) if onehot else None
     return graph
 
 

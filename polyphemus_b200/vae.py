@@ -149,13 +149,56 @@ class ContentEncoder(nn.Module):
         chord = self.chord_encoder(torch.cat((pitch, dur), dim=-1).view(k, t * self.d))
         return self.dropout_layer(F.relu(chord))
 
+    @staticmethod
+    def _bn_table(emb: nn.Linear, bn: nn.BatchNorm1d, ids: torch.Tensor, training: bool) -> torch.Tensor:
+        """BatchNorm(Linear(one_hot(ids))) as a [vocab, c] table.
+
+        A Linear applied to a one-hot row is a column of its weight plus the bias, so the rows BatchNorm sees
+        take only `vocab` distinct values: its batch statistics are the histogram-weighted statistics of those
+        values. Same function as model.py:357-362 / 369-376 (fp32 round-off aside), without materialising the
+        [N*15, 230] one-hot input or the [N*15, d/2] pre-norm activations.
+        """
+        table = emb.weight.float().t() + emb.bias.float()                       # [vocab, c]
+        use_batch_stats = training or bn.running_mean is None
+        if use_batch_stats:
+            n = ids.numel()
+            cnt = torch.bincount(ids.reshape(-1), minlength=table.size(0)).to(table.dtype)
+            mean = (cnt @ table) / n
+            var = (cnt @ (table - mean).square()) / n                           # biased, as BatchNorm normalises
+            if training and bn.running_mean is not None:
+                with torch.no_grad():
+                    m = bn.momentum if bn.momentum is not None else 0.1
+                    bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
+                    bn.running_var.mul_(1 - m).add_(var.detach() * (n / max(n - 1, 1)), alpha=m)
+                    bn.num_batches_tracked.add_(1)
+        else:
+            mean, var = bn.running_mean.float(), bn.running_var.float()
+        return (table - mean) * torch.rsqrt(var + bn.eps) * bn.weight.float() + bn.bias.float()
+
+    def _embed_ids(self, ids, pitch_emb, pitch_bn):
+        """ids int [k, 15, 2] (pitch id, duration id) -> chord embedding [k, d]; token-table form of `_embed`."""
+        k, t = ids.size(0), ids.size(1)
+        if k == 0:
+            return torch.zeros((0, self.d), dtype=torch.float32, device=ids.device)
+        p_ids, d_ids = ids[..., 0].long(), ids[..., 1].long()
+        pitch = F.embedding(p_ids, self._bn_table(pitch_emb, pitch_bn, p_ids, self.training))
+        dur = F.embedding(d_ids, self._bn_table(self.dur_emb, self.bn_dur, d_ids, self.training))
+        chord = self.chord_encoder(torch.cat((pitch, dur), dim=-1).view(k, t * self.d))
+        return self.dropout_layer(F.relu(chord))
+
     def forward(self, graph):
-        c = graph.c_tensor[:, 1:, :]                         # drop SOS
         perm, n_drum = _drum_split(graph)
-        drums = self._embed(c.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
-        others = self._embed(c.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
-        x = torch.empty((c.size(0), self.d), dtype=drums.dtype, device=drums.device)
-        x = x.index_copy(0, perm, torch.cat((drums, others), dim=0))
+        ids = getattr(graph, "c_tokens", None)
+        if ids is not None:                                    # dataset layout: token ids (preprocess.py:210)
+            ids = ids[:, 1:, :]                                # drop SOS
+            drums = self._embed_ids(ids.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
+            others = self._embed_ids(ids.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
+        else:                                                  # reference layout: one-hot float c_tensor
+            c = graph.c_tensor[:, 1:, :]
+            drums = self._embed(c.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
+            others = self._embed(c.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
+        x = torch.empty((perm.numel(), self.d), dtype=drums.dtype, device=drums.device)
+        x = x.index_copy(0, perm, torch.cat((drums, others.to(drums.dtype)), dim=0))
         graph.x = x.float()
         graph.distinct_bars = graph.bars + self.n_bars * graph.batch
         h = self.graph_encoder(graph)
@@ -238,11 +281,21 @@ class ContentDecoder(nn.Module):
         s.distinct_bars = s.bars + self.n_bars * s.batch
         s.x = z_bar.index_select(0, s.distinct_bars).float()        # every node starts from its bar's code
         h = self.graph_decoder(s)
-        h = self.dropout_layer(self.chord_decoder(h).view(-1, MAX_SIMU_TOKENS - 1, d))
+        # chord_decoder emits, per token slot, a pitch half and a duration half (model.py:549-567). Applying the
+        # two row-subsets of its weight separately gives the same numbers without slicing a [N, 15, d] activation
+        # (whose backward would zero-fill and copy two full-size tensors).
+        t = MAX_SIMU_TOKENS - 1
+        w = self.chord_decoder.weight.view(t, 2, half, d)
+        b = self.chord_decoder.bias.view(t, 2, half)
+        h_pitch = self.dropout_layer(F.linear(h, w[:, 0].reshape(t * half, d), b[:, 0].reshape(-1))).view(-1, t, half)
+        h_dur = self.dropout_layer(F.linear(h, w[:, 1].reshape(t * half, d), b[:, 1].reshape(-1))).view(-1, t, half)
         # both pitch heads on every node, then select per node: no compaction, no host sync
         is_drum = s.is_drum.view(-1, 1, 1)
-        pitch = torch.where(is_drum, self.drums_pitch_emb(h[..., :half]), self.non_drums_pitch_emb(h[..., :half]))
-        return torch.cat((pitch, self.dur_emb(h[..., half:])), dim=-1)
+        pitch = torch.where(is_drum, self.drums_pitch_emb(h_pitch), self.non_drums_pitch_emb(h_pitch))
+        dur = self.dur_emb(h_dur)
+        c_logits = torch.cat((pitch, dur), dim=-1)
+        c_logits._parts = (pitch, dur)          # lets the loss skip re-slicing the concatenation
+        return c_logits
 
 
 class Decoder(nn.Module):

@@ -132,18 +132,34 @@ def test_loss_restatement_matches_oracle():
             torch.testing.assert_close(gp[k], wp[k])
 
 
-def test_philox_host_matches_known_answer():
-    """Philox4x32-10 known-answer test (Random123 kat vectors): counter 0 / key 0 and all-ones."""
-    def philox(c, k):
-        M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
-        c, k = list(c), list(k)
-        for _ in range(10):
-            p0, p1 = M0 * c[0], M1 * c[2]
-            c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
-            k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
-        return c
-    assert philox([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
-    assert philox([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+def test_dropout_rng_known_answer():
+    """The dropout mask hashes a counter with the SplitMix64 output function (csrc/common.cuh). Known answers:
+    the first outputs of SplitMix64 seeded with 0 and with 1234567 (Vigna's reference implementation)."""
+    M = (1 << 64) - 1
+
+    def mix(z):
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+
+    def splitmix_stream(seed, n):
+        out, x = [], seed
+        for _ in range(n):
+            x = (x + 0x9E3779B97F4A7C15) & M
+            out.append(mix(x))
+        return out
+
+    assert splitmix_stream(0, 3) == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    assert splitmix_stream(1234567, 2) == [6457827717110365317, 3203168211198807973]
+
+    # our counter layout: bits(seed, eid, chunk) = mix(seed + GOLDEN * (1 + (eid << 32 | chunk))); with eid = 0 the
+    # chunk-th value of the stream seeded with `seed` — i.e. exactly SplitMix64.
+    def bits(seed, eid, chunk):
+        return mix((seed + 0x9E3779B97F4A7C15 * (((eid << 32) | chunk) + 1)) & M)
+
+    assert [bits(0, 0, c) for c in range(3)] == splitmix_stream(0, 3)
+    keep = [((bits(42, 7, 3) >> (16 * i)) & 0xFFFF) >= 6554 for i in range(4)]      # p = 0.1 -> thresh 6554
+    assert len(keep) == 4
 
 
 DP_SCRIPT = r"""

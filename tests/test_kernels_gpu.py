@@ -48,6 +48,16 @@ def ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def keep_bits(n_edges, d, p_drop, seed, cuda):
+    """Packed dropout keep-bits (pb_dropout_bits) or None when dropout is off."""
+    ffi = _ffi()
+    if not p_drop:
+        return None
+    bits = torch.empty(ffi.lib().pb_dropout_bits_bytes(n_edges, d) // 2, dtype=torch.int16, device=cuda)
+    ffi.check(ffi.lib().pb_dropout_bits(n_edges, d, p_drop, seed, ptr(bits), st()), "pb_dropout_bits")
+    return bits
+
+
 # ------------------------------------------------------------------------------------------------- GEMMs
 @pytest.mark.parametrize("dtype_name", ["bf16", "fp32"])
 @pytest.mark.parametrize("m,d", [(128, 64), (300, 128), (1000, 512), (4133, 256)])
@@ -164,7 +174,7 @@ def _oracle_h(x, arrays, table, keep=None, p=0.0):
     return (h / cnt.clamp(min=1).unsqueeze(1)).view(n, 6 * d)
 
 
-@pytest.mark.parametrize("d", [64, 256, 512])
+@pytest.mark.parametrize("d", [64, 192, 256, 512, 1024])
 @pytest.mark.parametrize("p_drop", [0.0, 0.1])
 def test_agg_fwd(cuda, d, p_drop):
     ffi = _ffi()
@@ -176,7 +186,8 @@ def test_agg_fwd(cuda, d, p_drop):
     x = torch.randn(n, d, generator=gen)
     nn_w, nn_b = torch.randn(d, 32, generator=gen) * 0.3, torch.randn(d, generator=gen) * 0.3
     table = torch.empty(32, d, device=cuda)
-    ffi.check(ffi.lib().pb_edge_table_fwd(ptr(nn_w.to(cuda)), ptr(nn_b.to(cuda)), d, ptr(table), st()), "table")
+    nn_w_dev, nn_b_dev = nn_w.to(cuda), nn_b.to(cuda)          # named: must outlive the asynchronous launch
+    ffi.check(ffi.lib().pb_edge_table_fwd(ptr(nn_w_dev), ptr(nn_b_dev), d, ptr(table), st()), "table")
     torch.testing.assert_close(table.cpu(), nn_w.t() + nn_b, rtol=0, atol=0)
     seed = 1234567
     keep = ops.dropout_keep_mask(arrays.edge_index.shape[1], d, p_drop, seed, cuda).cpu() if p_drop else None
@@ -185,23 +196,24 @@ def test_agg_fwd(cuda, d, p_drop):
     ref = torch.cat((_oracle_h(x.double(), arrays, table.cpu().double(), keep, p_drop), x.double()), 1)
     xd = x.to(cuda)
     a_hi, a_lo = torch.empty(n, k, device=cuda), torch.empty(n, k, device=cuda)
-    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_hi), ptr(a_lo), k, ffi.PB_F32, p_drop, seed,
+    bits = keep_bits(arrays.edge_index.shape[1], d, p_drop, seed, cuda)
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_hi), ptr(a_lo), k, ffi.PB_F32, ptr(bits), p_drop,
                                    st()), "agg_fwd")
-    torch.testing.assert_close((a_hi.double() + a_lo.double()).cpu(), ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close((a_hi.double() + a_lo.double()).cpu(), ref, rtol=2e-6, atol=1e-6)
     assert ((a_hi.view(torch.int32) & 8191) == 0).all()          # hi is a clean TF32 value
     a_bf = torch.empty(n, k, dtype=torch.bfloat16, device=cuda)
-    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_bf), None, k, ffi.PB_BF16, p_drop, seed,
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_bf), None, k, ffi.PB_BF16, ptr(bits), p_drop,
                                    st()), "agg_fwd")
     torch.testing.assert_close(a_bf.float().cpu(), ref.float(), rtol=8e-3, atol=1e-6)
     # bit-reproducible
     a2 = torch.empty_like(a_hi)
     l2 = torch.empty_like(a_lo)
-    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a2), ptr(l2), k, ffi.PB_F32, p_drop, seed,
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a2), ptr(l2), k, ffi.PB_F32, ptr(bits), p_drop,
                                    st()), "agg_fwd")
     assert torch.equal(a2, a_hi) and torch.equal(l2, a_lo)
 
 
-@pytest.mark.parametrize("d", [64, 256, 512, 1024])
+@pytest.mark.parametrize("d", [64, 192, 256, 512, 1024])
 @pytest.mark.parametrize("p_drop", [0.0, 0.1])
 def test_agg_bwd(cuda, d, p_drop):
     ffi = _ffi()
@@ -221,12 +233,13 @@ def test_agg_bwd(cuda, d, p_drop):
     gx_ref = x.grad + gy
     n_part = ffi.lib().pb_agg_bwd_num_partials()
     x_dev, t_dev, gy_dev = x.detach().float().to(cuda), table.detach().float().to(cuda), gy.float().to(cuda)
+    bits = keep_bits(arrays.edge_index.shape[1], d, p_drop, seed, cuda)
     for dtype, tol in ((ffi.PB_F32, dict(rtol=1e-5, atol=1e-5)), (ffi.PB_BF16, dict(rtol=2e-2, atol=2e-2))):
         da_dev = d_a.float().to(cuda) if dtype == ffi.PB_F32 else d_a.to(torch.bfloat16).to(cuda)
         gx = torch.empty(n, d, device=cuda)
         parts = torch.empty(n_part, 32, d, device=cuda)
         ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gx),
-                                       ptr(parts), p_drop, seed, st()), "agg_bwd")
+                                       ptr(parts), ptr(bits), p_drop, st()), "agg_bwd")
         torch.testing.assert_close(gx.double().cpu(), gx_ref, **tol)
         g_w, g_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
         ffi.check(ffi.lib().pb_edge_table_bwd(ptr(parts), n_part, d, ptr(g_w), ptr(g_b), st()), "table_bwd")
@@ -236,7 +249,7 @@ def test_agg_bwd(cuda, d, p_drop):
         if dtype == ffi.PB_F32:
             gx2, parts2 = torch.empty_like(gx), torch.empty_like(parts)
             ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev),
-                                           ptr(gx2), ptr(parts2), p_drop, seed, st()), "agg_bwd")
+                                           ptr(gx2), ptr(parts2), ptr(bits), p_drop, st()), "agg_bwd")
             assert torch.equal(gx, gx2) and torch.equal(parts, parts2)
 
 
@@ -325,3 +338,32 @@ def test_grad_prep(cuda):
     bf = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
     ffi.check(ffi.lib().pb_grad_prep(ptr(g), d, m, d, ffi.PB_BF16, ptr(bf), None, d, ptr(gb), ptr(ws), ws_bytes, st()), "prep")
     assert torch.equal(bf, g.to(torch.bfloat16))
+
+
+def test_dropout_mask_matches_host_definition(cuda):
+    """pb_dropout_mask == the documented counter hash: SplitMix64 mix of seed + GOLDEN*(1 + (eid<<32 | chunk)),
+    four 16-bit lanes per 4-channel chunk, keep iff lane >= round(p * 65536)."""
+    from polyphemus_b200 import ops
+
+    M = (1 << 64) - 1
+
+    def mix(z):
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        return z ^ (z >> 31)
+
+    n_edges, d, p, seed = 37, 64, 0.1, 0xDEADBEEF12345
+    got = ops.dropout_keep_mask(n_edges, d, p, seed, cuda).cpu().numpy()
+    thresh = int(p * 65536.0 + 0.5)
+    want = np.zeros((n_edges, d), dtype=bool)
+    for e in range(n_edges):
+        for c in range(d // 4):
+            r = mix((seed + 0x9E3779B97F4A7C15 * (((e << 32) | c) + 1)) & M)
+            for i in range(4):
+                want[e, 4 * c + i] = ((r >> (16 * i)) & 0xFFFF) >= thresh
+    np.testing.assert_array_equal(got, want)
+    big = ops.dropout_keep_mask(20000, 512, p, seed, cuda)
+    assert abs(float(big.float().mean()) - 0.9) < 2e-3
+    # neighbouring channels / edges are uncorrelated
+    b = big.float() - big.float().mean()
+    assert abs(float((b[:, :-1] * b[:, 1:]).mean())) < 1e-3 and abs(float((b[:-1] * b[1:]).mean())) < 1e-3

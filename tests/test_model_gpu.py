@@ -111,7 +111,12 @@ def test_gcn_stack_matches_reference_golden(cuda):
     torch.testing.assert_close(data.x.grad.cpu(), torch.from_numpy(ref["gx"]), rtol=1e-4, atol=1e-5)
     for name, p in gcn.named_parameters():
         want = torch.from_numpy(ref["grad." + name])
-        torch.testing.assert_close(p.grad.cpu(), want, rtol=1e-4, atol=1e-5 * max(1.0, float(want.abs().max())), msg=name)
+        atol = 1e-5 * max(1.0, float(want.abs().max()))
+        if name.endswith(".bias") and "norm_layers" not in name:
+            # a bias in front of BatchNorm has a mathematically zero gradient: both sides hold only the round-off
+            # of a cancelling column sum over |g_out| ~ 10, i.e. a few 1e-5
+            atol = 3e-4
+        torch.testing.assert_close(p.grad.cpu(), want, rtol=1e-4, atol=atol, msg=name)
     after = gcn.state_dict()
     for k in ref.files:
         if k.startswith("sd_after."):
@@ -175,12 +180,15 @@ def _vae_batch(ref, cuda):
     from polyphemus_b200.train import HostBatch, device_batch
 
     host = HostBatch(torch.from_numpy(ref["s_in"].copy()), torch.from_numpy(ref["tokens"].copy()))
-    return device_batch(host, cuda)
+    return device_batch(host, cuda, onehot=True)
 
 
-def test_vae_training_step_matches_reference_golden(cuda):
+@pytest.mark.parametrize("content", ["token_ids", "onehot"])
+def test_vae_training_step_matches_reference_golden(cuda, content):
     """Whole drop-in surface: VAE(graph) -> ((s_logits, c_logits), mu, log_var), reference loss, all gradients,
-    BatchNorm running statistics; inputs go through the device graph builder (one empty bar included)."""
+    BatchNorm running statistics; inputs go through the device graph builder (one empty bar included).
+    `content`: note tokens as ids (dataset layout, token-table embedding path) or as the reference's one-hot
+    float c_tensor (data.py:234-259, generic Linear + BatchNorm path)."""
     from polyphemus_b200.train import vae_losses
     import polyphemus_b200 as pb
 
@@ -189,14 +197,18 @@ def test_vae_training_step_matches_reference_golden(cuda):
         vae, cfg = _vae_from_golden(ref, cuda, "fp32")
         vae.train()
         graph = _vae_batch(ref, cuda)
+        tokens = graph.c_tokens
+        if content == "onehot":
+            graph.c_tokens = None
         (s_logits, c_logits), mu, log_var = vae(graph, noise=_t(ref["noise"], cuda))
-        torch.testing.assert_close(mu.detach().cpu(), torch.from_numpy(ref["mu"]), **TOL)
-        torch.testing.assert_close(log_var.detach().cpu(), torch.from_numpy(ref["log_var"]), **TOL)
+        # mu / log_var sit behind a BatchNorm over a batch of 4 sequences: reference self-noise level
+        torch.testing.assert_close(mu.detach().cpu(), torch.from_numpy(ref["mu"]), rtol=1e-4, atol=2e-5)
+        torch.testing.assert_close(log_var.detach().cpu(), torch.from_numpy(ref["log_var"]), rtol=1e-4, atol=2e-5)
         torch.testing.assert_close(s_logits.detach().cpu(), torch.from_numpy(ref["s_logits"]), **TOL)
         torch.testing.assert_close(c_logits.detach().cpu(), torch.from_numpy(ref["c_logits"]), rtol=1e-4, atol=2e-5)
         for use_tokens in (False, True):
             loss, parts = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_logits, mu, log_var, beta=0.0,
-                                     c_tokens=graph.c_tokens if use_tokens else None)
+                                     c_tokens=tokens if use_tokens else None)
             assert abs(float(loss) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
         got_parts = torch.stack([parts[k] for k in ("pitch", "dur", "structure", "kld")]).detach().cpu()
         torch.testing.assert_close(got_parts, torch.from_numpy(ref["loss_parts"]), rtol=1e-4, atol=1e-5)
@@ -229,7 +241,7 @@ def test_vae_bf16_mode_tracks_fp32(cuda):
         vae.train()
         graph = _vae_batch(ref, cuda)
         (s_logits, c_logits), mu, log_var = vae(graph, noise=_t(ref["noise"], cuda))
-        loss, _ = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_logits, mu, log_var)
+        loss, _ = vae_losses(graph.s_tensor, s_logits, None, c_logits, mu, log_var, c_tokens=graph.c_tokens)
         assert abs(float(loss) - float(ref["loss"])) < 2e-2 * abs(float(ref["loss"]))
         loss.backward()
         for key, mod in (("decoder.c_decoder.graph_decoder.layers.1.weight", vae.decoder.c_decoder.graph_decoder.layers[1].weight),
@@ -267,7 +279,7 @@ def test_vae_against_oracle_on_fresh_inputs(cuda):
     noise = torch.randn(6, cfg["d"], generator=torch.Generator().manual_seed(4))
     graph = device_batch(HostBatch(torch.from_numpy(arrays.s_tensor.copy()), tokens), cuda)
     (s_logits, c_logits), mu, log_var = vae(graph, noise=noise.to(cuda))
-    loss, _ = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_logits, mu, log_var)
+    loss, _ = vae_losses(graph.s_tensor, s_logits, None, c_logits, mu, log_var, c_tokens=graph.c_tokens)
     loss.backward()
     sd = mo.leaf_state(sd_cpu)
     gb = mo.make_batch(arrays, tokens.long())
