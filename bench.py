@@ -147,7 +147,7 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
     s = 2 if precision == "bf16" else 8        # bytes per GEMM-operand element (bf16, or TF32 hi+lo fp32 pair)
     s_da = 2 if precision == "bf16" else 4
     eb = 8 if p_drop > 0 else 4
-    parts = 444 * 32 * d * 4
+    parts = 1184 * d * 4                    # per-item partial rows of the edge-table gradient
     algo = {
         "pb_agg_fwd": ("hbm", n * d * 4 + eb * e + 4 * (n * r + 1) + 128 * d + n * k * s),
         "pb_agg_bwd": ("hbm", n * k * s_da + 2 * n * d * 4 + 16 * e + 4 * (n + 1) + n * d * 4 + 128 * d + parts),

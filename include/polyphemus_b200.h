@@ -46,7 +46,7 @@ enum pb_status {
  *   PB_BF16 : operands rounded to bf16, one tcgen05 kind::f16 MMA per k-step, fp32 accumulate. */
 enum pb_dtype { PB_F32 = 0, PB_BF16 = 1 };
 
-enum { PB_N_TRACKS = 4, PB_N_TIMESTEPS = 32, PB_N_DISTS = 32, PB_N_RELATIONS = 6 };
+enum { PB_N_TRACKS = 4, PB_N_TIMESTEPS = 32, PB_N_DISTS = 32, PB_N_RELATIONS = 6, PB_DIST_ITEMS = 1184 };
 
 int pb_version(void);
 const char* pb_last_error(void);
@@ -101,6 +101,9 @@ int pb_edge_attrs_decode(const float* edge_type, int64_t type_stride, const floa
  * edges inside a segment are ordered by their index in edge_index.
  *   in_ptr  i32 [N*R+1]   in_edge i32 [E] = src | dist<<26     in_eid i32 [E] original edge id
  *   out_ptr i32 [N+1]     out_rec int4 [E] = {dst, rel | dist<<8, eid, |segment(dst,rel)|}
+ * plus a grouping of the source-view positions by timestep distance, used by the deterministic reduction of the
+ * edge-network gradient: dist_perm i32 [E] (positions grouped by distance, stable), dist_items int4
+ * [PB_DIST_ITEMS] = {dist, begin, end, 0} (contiguous, similarly sized slices of dist_perm), dist_item_ptr i32 [33].
  * ---------------------------------------------------------------------------------------------- */
 typedef struct pb_csr {
   int64_t n_nodes;
@@ -112,22 +115,27 @@ typedef struct pb_csr {
   const int32_t* in_eid;
   const int32_t* out_ptr;
   const void* out_rec;
+  const int32_t* dist_perm;
+  const void* dist_items;
+  const int32_t* dist_item_ptr;
 } pb_csr_t;
 
 size_t pb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t n_relations);
+int32_t pb_csr_num_dist_items(void);
 int pb_csr_build(const int64_t* edge_index, const uint8_t* edge_type, const uint8_t* edge_dist,
                  int64_t n_nodes, int64_t n_edges, int32_t n_relations, int32_t* in_ptr, int32_t* in_edge,
-                 int32_t* in_eid, int32_t* out_ptr, void* out_rec, void* workspace, size_t workspace_bytes,
-                 pb_stream_t stream);
+                 int32_t* in_eid, int32_t* out_ptr, void* out_rec, int32_t* dist_perm, void* dist_items,
+                 int32_t* dist_item_ptr, void* workspace, size_t workspace_bytes, pb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Edge network table — replaces nn.Linear(32,d) applied to one-hot distances (model.py:127-129, 175):
- * T[k,:] = nn_weight[:,k] + nn_bias.   Backward (fixed-order reduction of the per-CTA partials of pb_agg_bwd):
+ * T[k,:] = nn_weight[:,k] + nn_bias.   Backward (fixed-order reduction of the per-item partials of pb_agg_bwd,
+ * f32 [PB_DIST_ITEMS, d], items of distance k = [dist_item_ptr[k], dist_item_ptr[k+1])):
  * g_nn_weight[c,k] = dT[k,c], g_nn_bias[c] = sum_k dT[k,c].
  * ---------------------------------------------------------------------------------------------- */
 int pb_edge_table_fwd(const float* nn_weight, const float* nn_bias, int32_t d, float* table,
                       pb_stream_t stream);
-int pb_edge_table_bwd(const float* dtable_partials, int32_t n_partials, int32_t d, float* g_nn_weight,
+int pb_edge_table_bwd(const float* dtable_partials, const int32_t* dist_item_ptr, int32_t d, float* g_nn_weight,
                       float* g_nn_bias, pb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -140,16 +148,19 @@ int pb_edge_table_bwd(const float* dtable_partials, int32_t n_partials, int32_t 
  * 4-channel chunk, keep iff lane >= round(p * 65536) — packed 1 bit per channel, and read by forward, operand
  * recompute and backward alike (keep_bits may be NULL when p_drop == 0). pb_dropout_mask exposes the same
  * decisions as bytes [E, d] for checking.
- * Backward: gx[u] = gy_res[u] + dA[u, R*d:] + sum_{e: src=u} dH[dst_e, rel_e]/cnt * keep * 1[x*T>0] * T[dist_e]
- *           dT partials per CTA (deterministic, reduced by pb_edge_table_bwd).
+ * Backward, two kernels, no atomics:
+ *   (1) one warp per source node u: gx[u] = gy_res[u] + dA[u, R*d:] + sum_{e: src=u} ds_e * T[dist_e] with
+ *       ds_e = dH[dst_e, rel_e]/cnt * keep * 1[x*T>0]; the table-gradient row q_e = ds_e * x[u] of every out-edge
+ *       position goes to q_buf [E, d] (bf16 for PB_BF16, f32 for PB_F32);
+ *   (2) the rows of q_buf are summed per timestep distance through dist_perm / dist_items (fixed order) into
+ *       dtable_partials f32 [PB_DIST_ITEMS, d], which pb_edge_table_bwd finishes.
  * ---------------------------------------------------------------------------------------------- */
 size_t pb_dropout_bits_bytes(int64_t n_edges, int32_t d);
 int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, void* keep_bits, pb_stream_t stream);
 int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, void* a_hi, void* a_lo,
                int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, pb_stream_t stream);
-int32_t pb_agg_bwd_num_partials(void);
 int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
-               int64_t ldda, int32_t dtype, const float* gy_res, float* gx, float* dtable_partials,
+               int64_t ldda, int32_t dtype, const float* gy_res, float* gx, void* q_buf, float* dtable_partials,
                const void* keep_bits, float p_drop, pb_stream_t stream);
 int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep /*[E,d]*/,
                     pb_stream_t stream);

@@ -28,7 +28,7 @@ class CsrStruct(Structure):
     _fields_ = [
         ("n_nodes", c_int64), ("n_edges", c_int64), ("n_relations", c_int32), ("reserved", c_int32),
         ("in_ptr", c_void_p), ("in_edge", c_void_p), ("in_eid", c_void_p), ("out_ptr", c_void_p),
-        ("out_rec", c_void_p),
+        ("out_rec", c_void_p), ("dist_perm", c_void_p), ("dist_items", c_void_p), ("dist_item_ptr", c_void_p),
     ]
 
 
@@ -44,14 +44,14 @@ SIGNATURES = {
     "pb_edge_attrs_encode": (c_int, [_P, _P, c_int64, _P, _P]),
     "pb_edge_attrs_decode": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
     "pb_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
-    "pb_csr_build": (c_int, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pb_csr_num_dist_items": (c_int32, []),
+    "pb_csr_build": (c_int, [_P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pb_edge_table_fwd": (c_int, [_P, _P, c_int32, _P, _P]),
-    "pb_edge_table_bwd": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
+    "pb_edge_table_bwd": (c_int, [_P, _P, c_int32, _P, _P, _P]),
     "pb_dropout_bits_bytes": (c_size_t, [c_int64, c_int32]),
     "pb_dropout_bits": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
     "pb_agg_fwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, c_float, _P]),
-    "pb_agg_bwd_num_partials": (c_int32, []),
-    "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_float, _P]),
+    "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, _P]),
     "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
@@ -95,8 +95,8 @@ def lib() -> ctypes.CDLL:
 # the library goes through `call`, so `launch_counter` is the number of OUR kernels launched (memsets and
 # host-only queries are not counted).
 LAUNCHES = {
-    "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 10,
-    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 1, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
+    "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
+    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,

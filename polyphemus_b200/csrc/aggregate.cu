@@ -22,18 +22,18 @@ __global__ void edge_table_fwd_kernel(const float* __restrict__ w, const float* 
   table[i] = w[c * PB_N_DISTS + k] + b[c];
 }
 
-// partials [P][32][d] -> g_w [d][32], g_b [d]; fixed summation order (p ascending, then k ascending)
-__global__ void __launch_bounds__(1024) edge_table_bwd_kernel(const float* __restrict__ partials, int n_partials,
-                                                              int d, float* __restrict__ g_w,
-                                                              float* __restrict__ g_b) {
+// partials [PB_DIST_ITEMS][d] (one row per work item, items of distance k = [item_ptr[k], item_ptr[k+1])) ->
+// g_w [d][32], g_b [d]; fixed summation order (item ascending, then k ascending)
+__global__ void __launch_bounds__(1024) edge_table_bwd_kernel(const float* __restrict__ partials,
+                                                              const int* __restrict__ item_ptr, int d,
+                                                              float* __restrict__ g_w, float* __restrict__ g_b) {
   __shared__ float tile[32][33];
   const int ci = threadIdx.x, k = threadIdx.y;
   const int c = blockIdx.x * 32 + ci;
   float s = 0.f;
   if (c < d) {
-    const float* p = partials + (size_t)k * d + c;
-    const size_t stride = (size_t)PB_N_DISTS * d;
-    for (int i = 0; i < n_partials; ++i) s += p[i * stride];
+    const int i0 = __ldg(item_ptr + k), i1 = __ldg(item_ptr + k + 1);
+    for (int i = i0; i < i1; ++i) s += partials[(size_t)i * d + c];
     g_w[(size_t)c * PB_N_DISTS + k] = s;
   }
   tile[k][ci] = s;
@@ -194,9 +194,6 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-constexpr int kBwdThreads = 128;
-constexpr int kBwdPartials = 444;  // 3 CTAs on each of 148 SMs; fixed so the reduction order never changes
-
 template <bool BF16>
 __device__ __forceinline__ float4 load_grad4(const void* d_a, size_t elem_off) {
   if constexpr (BF16) {
@@ -207,154 +204,125 @@ __device__ __forceinline__ float4 load_grad4(const void* d_a, size_t elem_off) {
     return ldg4(reinterpret_cast<const float*>(d_a) + elem_off);
   }
 }
+template <bool BF16>
+__device__ __forceinline__ void store_q(void* q, size_t elem_off, float4 v) {
+  if constexpr (BF16)
+    st_stream2(reinterpret_cast<__nv_bfloat16*>(q) + elem_off, make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)));
+  else
+    st_stream4(reinterpret_cast<float*>(q) + elem_off, v);
+}
 
-// Scatter-by-source without atomics: each node u gathers the gradients of the segments its out-edges feed.
-// A CTA owns a contiguous node range; thread t owns channel chunks (fixed), so the per-distance table
-// gradient accumulates in shared memory with a fixed order per address -> deterministic.
-//   TPN  threads per node (d/4 capped at 128), G = 128/TPN nodes processed concurrently per CTA
-//   CPT  float4 chunks per thread (d/512 when d > 512)
-// Software pipeline: while node u is processed, the rows and edge records of the CTA's next node are in
-// flight; inside a node the gathers of up to kBatch edges are issued before any of them is consumed.
-template <bool BF16, bool DROPOUT, int CPT>
-__global__ void __launch_bounds__(kBwdThreads) agg_bwd_kernel(
+// (1) Scatter-by-source without atomics: one warp per source node u gathers the gradients of the segments its
+// out-edges feed (same shape as the forward: coalesced record load, shuffles, 16-byte row gathers, full occupancy)
+// and emits, per out-edge position, the row q_e = ds_e * x[u] that the edge-table gradient needs.
+template <bool BF16, bool DROPOUT, int CPL, bool EXACT>
+__global__ void __launch_bounds__(256) agg_bwd_dx_kernel(
     const int* __restrict__ out_ptr, const int4* __restrict__ out_rec, const float* __restrict__ x,
     const float* __restrict__ table, const void* __restrict__ d_a, int64_t ldda, const float* __restrict__ gy_res,
-    float* __restrict__ gx, float* __restrict__ dt_partials, int64_t n_nodes, int d, int n_rel, int tpn,
+    float* __restrict__ gx, void* __restrict__ q_buf, int64_t n_nodes, int d, int n_rel,
     const uint16_t* __restrict__ keep_bits, float keep_scale) {
-  extern __shared__ float dts[];  // [G][32][d]
-  const int groups = kBwdThreads / tpn;
-  const int g = threadIdx.x / tpn, tc = threadIdx.x % tpn;
-  const int sw = tpn < 32 ? tpn : 32;          // shuffle width: threads of one node inside a warp
-  const int sl = (threadIdx.x & 31) % sw;      // lane inside that sub-warp
-  const uint32_t smask = sw >= 32 ? 0xffffffffu : (((1u << sw) - 1u) << (((threadIdx.x & 31) / sw) * sw));
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int G16 = (CPL + 3) / 4;
+  const int lane = threadIdx.x & 31;
   const int nchunk = d >> 2;
-  const int g16 = (d + 511) / 512;
-  for (int i = threadIdx.x; i < groups * PB_N_DISTS * d; i += kBwdThreads) dts[i] = 0.f;
-  __syncthreads();
-  float* my_dt = dts + (size_t)g * PB_N_DISTS * d;
-
-  const int64_t per_cta = (n_nodes + gridDim.x - 1) / gridDim.x;
-  const int64_t first = (int64_t)blockIdx.x * per_cta;
-  const int64_t last = first + per_cta < n_nodes ? first + per_cta : n_nodes;
-
-  constexpr int kBatch = 8;   // divides the shuffle width (16 or 32)
-  struct NodeData {
-    float4 xu[CPT], acc[CPT];
-    int beg, end;
-    int4 rec;
-  };
-  auto load_rows = [&](int64_t u, NodeData& nd) {
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_nodes; u += n_warps) {
+    const int my_ptr = lane < 2 ? __ldg(out_ptr + u + lane) : 0;
+    const int beg = __shfl_sync(kFull, my_ptr, 0), end = __shfl_sync(kFull, my_ptr, 1);
+    int base = beg;
+    int4 my_rec = base + lane < end ? __ldg(out_rec + base + lane) : make_int4(0, 0, 0, 0);
+    float4 xu[CPL], acc[CPL];
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = tc + tpn * j;
-      if (c < nchunk) {
-        nd.xu[j] = ldg4(x + (size_t)u * d + 4 * c);
-        nd.acc[j] = load_grad4<BF16>(d_a, (size_t)u * ldda + (size_t)n_rel * d + 4 * c);  // root branch
+    for (int j = 0; j < CPL; ++j) {
+      if (EXACT || lane + 32 * j < nchunk) {
+        const size_t c4 = 4 * (size_t)(lane + 32 * j);
+        xu[j] = ldg4(x + (size_t)u * d + c4);
+        acc[j] = load_grad4<BF16>(d_a, (size_t)u * ldda + (size_t)n_rel * d + c4);   // root branch
         if (gy_res) {
-          const float4 r = ldg4(gy_res + (size_t)u * d + 4 * c);  // residual branch
-          nd.acc[j].x += r.x; nd.acc[j].y += r.y; nd.acc[j].z += r.z; nd.acc[j].w += r.w;
+          const float4 r = ld_stream4(gy_res + (size_t)u * d + c4);                   // residual branch
+          acc[j].x += r.x; acc[j].y += r.y; acc[j].z += r.z; acc[j].w += r.w;
         }
       }
     }
-    nd.beg = __ldg(out_ptr + u);
-    nd.end = __ldg(out_ptr + u + 1);
-  };
-  auto load_recs = [&](int base, int end) {
-    return base + sl < end ? __ldg(out_rec + base + sl) : make_int4(0, 0, 0, 0);
-  };
+    for (int i = beg; i < end; ++i) {
+      if (i - base == 32) {  // warp-uniform (out-degree > 32 only)
+        base = i;
+        my_rec = base + lane < end ? __ldg(out_rec + base + lane) : make_int4(0, 0, 0, 0);
+      }
+      const int dst = __shfl_sync(kFull, my_rec.x, i - base);
+      const int meta = __shfl_sync(kFull, my_rec.y, i - base);
+      const int cnt = __shfl_sync(kFull, my_rec.w, i - base);
+      const size_t goff = (size_t)dst * ldda + (size_t)(meta & 0xff) * d + 4 * lane;
+      const float* trow = table + (size_t)(meta >> 8) * d + 4 * lane;
+      uint32_t kw[G16];
+      if constexpr (DROPOUT) {
+        const uint32_t eid = (uint32_t)__shfl_sync(kFull, my_rec.z, i - base);
+#pragma unroll
+        for (int q = 0; q < G16; ++q) kw[q] = __ldg(keep_bits + ((size_t)eid * G16 + q) * 32 + lane);
+      }
+      // d(mean)/d(sum) = 1/|segment| (one reciprocal per edge), times the dropout scale
+      float coef = cnt > 1 ? 1.0f / (float)cnt : 1.0f;
+      if constexpr (DROPOUT) coef *= keep_scale;
+      const size_t qrow = (size_t)i * d + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        if (EXACT || lane + 32 * j < nchunk) {
+          float4 ds = load_grad4<BF16>(d_a, goff + 128 * j);
+          const float4 t = ldg4(trow + 128 * j);
+          const float4 xv = xu[j];
+          uint32_t nib = 0xFu;
+          if constexpr (DROPOUT) nib = kw[j >> 2] >> (4 * (j & 3));
+          ds.x = ((nib & 1u) && xv.x * t.x > 0.f) ? ds.x * coef : 0.f;
+          ds.y = ((nib & 2u) && xv.y * t.y > 0.f) ? ds.y * coef : 0.f;
+          ds.z = ((nib & 4u) && xv.z * t.z > 0.f) ? ds.z * coef : 0.f;
+          ds.w = ((nib & 8u) && xv.w * t.w > 0.f) ? ds.w * coef : 0.f;
+          acc[j].x += ds.x * t.x; acc[j].y += ds.y * t.y; acc[j].z += ds.z * t.z; acc[j].w += ds.w * t.w;
+          store_q<BF16>(q_buf, qrow + 128 * j, make_float4(ds.x * xv.x, ds.y * xv.y, ds.z * xv.z, ds.w * xv.w));
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+      if (EXACT || lane + 32 * j < nchunk) st_stream4(gx + (size_t)u * d + 4 * (lane + 32 * j), acc[j]);
+  }
+}
 
-  NodeData cur;
-  int64_t u = first + g;
-  if (u < last) {
-    load_rows(u, cur);
-    cur.rec = load_recs(cur.beg, cur.end);
+// (2) Edge-table gradient: dT[k] = sum of the q rows whose edge has distance k. One CTA per work item (a slice
+// of dist_perm inside one distance group); thread = channel chunk, rows added in slice order -> deterministic.
+constexpr int kQThreads = 128;
+template <bool BF16, int CPT>
+__global__ void __launch_bounds__(kQThreads) dist_reduce_kernel(const void* __restrict__ q_buf,
+                                                                const int* __restrict__ dist_perm,
+                                                                const int4* __restrict__ items, int d,
+                                                                float* __restrict__ partials) {
+  const int4 it = __ldg(items + blockIdx.x);   // {dist, begin, end, 0}
+  const int nchunk = d >> 2;
+  float4 acc[CPT];
+#pragma unroll
+  for (int j = 0; j < CPT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int kRows = 8;
+  for (int r0 = it.y; r0 < it.z; r0 += kRows) {
+    int pos[kRows];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i) pos[i] = r0 + i < it.z ? __ldg(dist_perm + r0 + i) : -1;
+    float4 v[kRows][CPT];
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        const int c = threadIdx.x + kQThreads * j;
+        v[i][j] = (pos[i] >= 0 && c < nchunk) ? load_grad4<BF16>(q_buf, (size_t)pos[i] * d + 4 * c)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+    for (int i = 0; i < kRows; ++i)
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) { acc[j].x += v[i][j].x; acc[j].y += v[i][j].y; acc[j].z += v[i][j].z; acc[j].w += v[i][j].w; }
   }
-  while (u < last) {
-    const int64_t un = u + groups;
-    NodeData nxt;
-    if (un < last) load_rows(un, nxt);
-    int base = cur.beg;
-    int4 my_rec = cur.rec;
-    for (int b0 = cur.beg; b0 < cur.end; b0 += kBatch) {
-      if (b0 - base == sw) {  // uniform across the node's threads (degree > shuffle width only)
-        base = b0;
-        my_rec = load_recs(base, cur.end);
-      }
-      const int nb = cur.end - b0 < kBatch ? cur.end - b0 : kBatch;
-      float4 dh[kBatch][CPT];
-      uint32_t nibs[kBatch];
 #pragma unroll
-      for (int i = 0; i < kBatch; ++i) {   // issue every gather of the batch before any of them is consumed
-        const int dst = __shfl_sync(smask, my_rec.x, b0 - base + i, sw);
-        const int meta = __shfl_sync(smask, my_rec.y, b0 - base + i, sw);
-        const uint32_t eid = (uint32_t)__shfl_sync(smask, my_rec.z, b0 - base + i, sw);
-        nibs[i] = 0xFFFFFFFFu;
-        if (i < nb) {
-          const size_t off = (size_t)dst * ldda + (size_t)(meta & 0xff) * d;
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) {
-            const int c = tc + tpn * j;
-            if (c < nchunk) dh[i][j] = load_grad4<BF16>(d_a, off + 4 * c);
-          }
-          if constexpr (DROPOUT) {
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < CPT; ++j) {
-              const int c = tc + tpn * j;
-              if (c < nchunk) w |= keep_nibble(keep_bits, g16, eid, c) << (4 * j);
-            }
-            nibs[i] = w;
-          }
-        }
-      }
-      if (b0 == cur.beg && un < last) nxt.rec = load_recs(nxt.beg, nxt.end);   // next node's records, behind the gathers
-#pragma unroll
-      for (int i = 0; i < kBatch; ++i) {
-        const int meta = __shfl_sync(smask, my_rec.y, b0 - base + i, sw);
-        const int cnt = __shfl_sync(smask, my_rec.w, b0 - base + i, sw);
-        if (i < nb) {
-          const int dist = meta >> 8;
-          // d(mean)/d(sum) = 1/|segment| (one reciprocal per edge), times the dropout scale
-          float coef = cnt > 1 ? 1.0f / (float)cnt : 1.0f;
-          if constexpr (DROPOUT) coef *= keep_scale;
-#pragma unroll
-          for (int j = 0; j < CPT; ++j) {
-            const int c = tc + tpn * j;
-            if (c < nchunk) {
-              const float4 t = ldg4(table + (size_t)dist * d + 4 * c);
-              const float4 xv = cur.xu[j];
-              const uint32_t nib = nibs[i] >> (4 * j);
-              float4 ds = dh[i][j];
-              ds.x = ((nib & 1u) && xv.x * t.x > 0.f) ? ds.x * coef : 0.f;
-              ds.y = ((nib & 2u) && xv.y * t.y > 0.f) ? ds.y * coef : 0.f;
-              ds.z = ((nib & 4u) && xv.z * t.z > 0.f) ? ds.z * coef : 0.f;
-              ds.w = ((nib & 8u) && xv.w * t.w > 0.f) ? ds.w * coef : 0.f;
-              cur.acc[j].x += ds.x * t.x; cur.acc[j].y += ds.y * t.y;
-              cur.acc[j].z += ds.z * t.z; cur.acc[j].w += ds.w * t.w;
-              float4* slot = reinterpret_cast<float4*>(my_dt + (size_t)dist * d + 4 * c);
-              float4 acc_t = *slot;
-              acc_t.x += ds.x * xv.x; acc_t.y += ds.y * xv.y; acc_t.z += ds.z * xv.z; acc_t.w += ds.w * xv.w;
-              *slot = acc_t;
-            }
-          }
-        }
-      }
-    }
-    if (cur.beg == cur.end && un < last) nxt.rec = load_recs(nxt.beg, nxt.end);   // isolated node: no batch ran
-#pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      const int c = tc + tpn * j;
-      if (c < nchunk) st_stream4(gx + (size_t)u * d + 4 * c, cur.acc[j]);
-    }
-    cur = nxt;
-    u = un;
-  }
-  __syncthreads();
-  float* out = dt_partials + (size_t)blockIdx.x * PB_N_DISTS * d;
-  for (int i = threadIdx.x; i < PB_N_DISTS * d; i += kBwdThreads) {
-    float s = 0.f;
-    for (int gg = 0; gg < groups; ++gg) s += dts[(size_t)gg * PB_N_DISTS * d + i];
-    out[i] = s;
+  for (int j = 0; j < CPT; ++j) {
+    const int c = threadIdx.x + kQThreads * j;
+    if (c < nchunk) reinterpret_cast<float4*>(partials + (size_t)blockIdx.x * d)[c] = acc[j];
   }
 }
 
@@ -378,10 +346,10 @@ extern "C" int pb_edge_table_fwd(const float* nn_weight, const float* nn_bias, i
   return PB_OK;
 }
 
-extern "C" int pb_edge_table_bwd(const float* dtable_partials, int32_t n_partials, int32_t d, float* g_nn_weight,
-                                 float* g_nn_bias, pb_stream_t stream) {
-  PB_REQUIRE(dtable_partials && g_nn_weight && g_nn_bias && n_partials > 0 && d > 0, "pb_edge_table_bwd: bad arguments");
-  edge_table_bwd_kernel<<<(d + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(dtable_partials, n_partials, d,
+extern "C" int pb_edge_table_bwd(const float* dtable_partials, const int32_t* dist_item_ptr, int32_t d,
+                                 float* g_nn_weight, float* g_nn_bias, pb_stream_t stream) {
+  PB_REQUIRE(dtable_partials && dist_item_ptr && g_nn_weight && g_nn_bias && d > 0, "pb_edge_table_bwd: bad arguments");
+  edge_table_bwd_kernel<<<(d + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(dtable_partials, dist_item_ptr, d,
                                                                                g_nn_weight, g_nn_bias);
   PB_LAUNCH_CHECK();
   return PB_OK;
@@ -452,38 +420,48 @@ extern "C" int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const 
               : launch_agg_fwd<false, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
 }
 
-extern "C" int32_t pb_agg_bwd_num_partials(void) { return kBwdPartials; }
-
 template <bool BF16, bool DROP>
 static int launch_agg_bwd(const pb_csr_t* g, const float* x, int d, const float* table, const void* d_a, int64_t ldda,
-                          const float* gy_res, float* gx, float* dtp, const uint16_t* bits, float scale,
+                          const float* gy_res, float* gx, void* q_buf, float* dtp, const uint16_t* bits, float scale,
                           cudaStream_t st) {
-  int tpn = 1;                                   // threads per node: largest power of two <= min(128, d/4)
-  while (tpn * 2 <= std::min(kBwdThreads, d / 4)) tpn *= 2;
-  const int groups = kBwdThreads / tpn;
-  const int cpt = (d / 4 + tpn - 1) / tpn;
-  const size_t smem = (size_t)groups * PB_N_DISTS * d * sizeof(float);
-#define PB_AGG_BWD(CPT)                                                                                          \
-  do {                                                                                                           \
-    PB_CUDA(cudaFuncSetAttribute(agg_bwd_kernel<BF16, DROP, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                 (int)smem));                                                                    \
-    agg_bwd_kernel<BF16, DROP, CPT><<<kBwdPartials, kBwdThreads, smem, st>>>(                                    \
-        g->out_ptr, reinterpret_cast<const int4*>(g->out_rec), x, table, d_a, ldda, gy_res, gx, dtp, g->n_nodes, \
-        d, g->n_relations, tpn, bits, scale);                                                                    \
-  } while (0)
-  if (cpt <= 1) PB_AGG_BWD(1);
-  else PB_AGG_BWD(2);
+  const int cpl = (d + 127) / 128;
+  const bool exact = d % 128 == 0 && (cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8);
+  const int threads = 256;
+  const int64_t want = (g->n_nodes * 32 + threads - 1) / threads;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8 * 4));
+  const int4* recs = reinterpret_cast<const int4*>(g->out_rec);
+#define PB_AGG_BWD(CPL, EX)                                                                                        \
+  agg_bwd_dx_kernel<BF16, DROP, CPL, EX><<<grid, threads, 0, st>>>(g->out_ptr, recs, x, table, d_a, ldda, gy_res,   \
+                                                                   gx, q_buf, g->n_nodes, d, g->n_relations, bits, scale)
+  if (exact) {
+    if (cpl == 1) PB_AGG_BWD(1, true);
+    else if (cpl == 2) PB_AGG_BWD(2, true);
+    else if (cpl == 4) PB_AGG_BWD(4, true);
+    else PB_AGG_BWD(8, true);
+  } else {
+    if (cpl <= 1) PB_AGG_BWD(1, false);
+    else if (cpl <= 2) PB_AGG_BWD(2, false);
+    else if (cpl <= 4) PB_AGG_BWD(4, false);
+    else PB_AGG_BWD(8, false);
+  }
 #undef PB_AGG_BWD
+  PB_LAUNCH_CHECK();
+  const int4* items = reinterpret_cast<const int4*>(g->dist_items);
+  if (d <= 4 * kQThreads)
+    dist_reduce_kernel<BF16, 1><<<PB_DIST_ITEMS, kQThreads, 0, st>>>(q_buf, g->dist_perm, items, d, dtp);
+  else
+    dist_reduce_kernel<BF16, 2><<<PB_DIST_ITEMS, kQThreads, 0, st>>>(q_buf, g->dist_perm, items, d, dtp);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
 
 extern "C" int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
-                          int64_t ldda, int32_t dtype, const float* gy_res, float* gx, float* dtable_partials,
-                          const void* keep_bits, float p_drop, pb_stream_t stream) {
+                          int64_t ldda, int32_t dtype, const float* gy_res, float* gx, void* q_buf,
+                          float* dtable_partials, const void* keep_bits, float p_drop, pb_stream_t stream) {
   int rc = check_csr(csr, d, "pb_agg_bwd");
   if (rc) return rc;
-  PB_REQUIRE(x && table && d_a && gx && dtable_partials, "pb_agg_bwd: null pointer");
+  PB_REQUIRE(x && table && d_a && gx && q_buf && dtable_partials, "pb_agg_bwd: null pointer");
+  PB_REQUIRE(csr->dist_perm && csr->dist_items && csr->dist_item_ptr, "pb_agg_bwd: CSR plan lacks the distance grouping");
   PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "pb_agg_bwd: bad dtype");
   PB_REQUIRE(ldda >= (int64_t)(csr->n_relations + 1) * d && ldda % 8 == 0, "pb_agg_bwd: bad ldda");
   PB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "pb_agg_bwd: p_drop out of range");
@@ -492,10 +470,10 @@ extern "C" int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const 
   const uint16_t* bits = p_drop > 0.f ? reinterpret_cast<const uint16_t*>(keep_bits) : nullptr;
   const float scale = 1.f / (1.f - p_drop);
   if (dtype == PB_BF16)
-    return bits ? launch_agg_bwd<true, true>(csr, x, d, table, d_a, ldda, gy_res, gx, dtable_partials, bits, scale, st)
-                : launch_agg_bwd<true, false>(csr, x, d, table, d_a, ldda, gy_res, gx, dtable_partials, bits, scale, st);
-  return bits ? launch_agg_bwd<false, true>(csr, x, d, table, d_a, ldda, gy_res, gx, dtable_partials, bits, scale, st)
-              : launch_agg_bwd<false, false>(csr, x, d, table, d_a, ldda, gy_res, gx, dtable_partials, bits, scale, st);
+    return bits ? launch_agg_bwd<true, true>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st)
+                : launch_agg_bwd<true, false>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st);
+  return bits ? launch_agg_bwd<false, true>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st)
+              : launch_agg_bwd<false, false>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st);
 }
 
 extern "C" int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep,

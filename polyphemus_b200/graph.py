@@ -42,15 +42,22 @@ class CsrPlan:
         self.in_eid = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
         self.out_ptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
         self.out_rec = torch.empty((max(e, 1), 4), dtype=torch.int32, device=dev)
+        self.n_dist_items = int(lib.pb_csr_num_dist_items())
+        self.dist_perm = torch.empty(max(e, 1), dtype=torch.int32, device=dev)
+        self.dist_items = torch.empty((self.n_dist_items, 4), dtype=torch.int32, device=dev)
+        self.dist_item_ptr = torch.empty(_ffi.N_DISTS + 1, dtype=torch.int32, device=dev)
         ws_bytes = lib.pb_csr_workspace_bytes(n, e, r)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _ffi.call("pb_csr_build", edge_index.data_ptr(), edge_type.data_ptr(), edge_dist.data_ptr(), n, e, r,
                       self.in_ptr.data_ptr(), self.in_edge.data_ptr(), self.in_eid.data_ptr(),
-                      self.out_ptr.data_ptr(), self.out_rec.data_ptr(), ws.data_ptr(), ws_bytes, _ffi.stream())
+                      self.out_ptr.data_ptr(), self.out_rec.data_ptr(), self.dist_perm.data_ptr(),
+                      self.dist_items.data_ptr(), self.dist_item_ptr.data_ptr(), ws.data_ptr(), ws_bytes, _ffi.stream())
         self.device = dev
         self.struct = _ffi.CsrStruct(n, e, r, 0, self.in_ptr.data_ptr(), self.in_edge.data_ptr(),
-                                     self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr())
+                                     self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr(),
+                                     self.dist_perm.data_ptr(), self.dist_items.data_ptr(),
+                                     self.dist_item_ptr.data_ptr())
 
     def ref(self):
         return ctypes.byref(self.struct)

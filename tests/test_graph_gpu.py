@@ -148,6 +148,23 @@ def test_csr_plan_matches_edge_list(cuda):
     np.testing.assert_array_equal(rec[:e, 2], order_o)
     seg_len = np.bincount(key, minlength=n * 6)
     np.testing.assert_array_equal(rec[:e, 3], seg_len[key[order_o]])
+    # grouping of the out-edge positions by timestep distance (stable) + its work items
+    dist_of_pos = ed[order_o]
+    perm = plan.dist_perm.cpu().numpy()[:e]
+    np.testing.assert_array_equal(perm, np.lexsort((np.arange(e), dist_of_pos)))
+    items = plan.dist_items.cpu().numpy()
+    item_ptr = plan.dist_item_ptr.cpu().numpy()
+    counts = np.bincount(dist_of_pos, minlength=32)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    assert item_ptr[0] == 0 and item_ptr[32] <= plan.n_dist_items
+    for kk in range(32):
+        its = items[item_ptr[kk]:item_ptr[kk + 1]]
+        if counts[kk] == 0:
+            assert len(its) == 0
+            continue
+        assert (its[:, 0] == kk).all() and its[0, 1] == starts[kk] and its[-1, 2] == starts[kk + 1]
+        assert (its[1:, 1] == its[:-1, 2]).all() and (its[:, 2] > its[:, 1]).all()
+    assert (items[item_ptr[32]:, 1] == items[item_ptr[32]:, 2]).all()
 
 
 def test_graph_build_is_deterministic(cuda):

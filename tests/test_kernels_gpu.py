@@ -231,25 +231,27 @@ def test_agg_bwd(cuda, d, p_drop):
     a_ref = torch.cat((_oracle_h(x, arrays, table, keep, p_drop), x), 1)
     (a_ref * d_a).sum().backward()
     gx_ref = x.grad + gy
-    n_part = ffi.lib().pb_agg_bwd_num_partials()
+    n_items = g.plan.n_dist_items
     x_dev, t_dev, gy_dev = x.detach().float().to(cuda), table.detach().float().to(cuda), gy.float().to(cuda)
     bits = keep_bits(arrays.edge_index.shape[1], d, p_drop, seed, cuda)
+    n_edges = arrays.edge_index.shape[1]
     for dtype, tol in ((ffi.PB_F32, dict(rtol=1e-5, atol=1e-5)), (ffi.PB_BF16, dict(rtol=2e-2, atol=2e-2))):
         da_dev = d_a.float().to(cuda) if dtype == ffi.PB_F32 else d_a.to(torch.bfloat16).to(cuda)
         gx = torch.empty(n, d, device=cuda)
-        parts = torch.empty(n_part, 32, d, device=cuda)
+        q_buf = torch.empty(n_edges, d, dtype=da_dev.dtype, device=cuda)
+        parts = torch.empty(n_items, d, device=cuda)
         ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gx),
-                                       ptr(parts), ptr(bits), p_drop, st()), "agg_bwd")
+                                       ptr(q_buf), ptr(parts), ptr(bits), p_drop, st()), "agg_bwd")
         torch.testing.assert_close(gx.double().cpu(), gx_ref, **tol)
         g_w, g_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
-        ffi.check(ffi.lib().pb_edge_table_bwd(ptr(parts), n_part, d, ptr(g_w), ptr(g_b), st()), "table_bwd")
+        ffi.check(ffi.lib().pb_edge_table_bwd(ptr(parts), ptr(g.plan.dist_item_ptr), d, ptr(g_w), ptr(g_b), st()), "table_bwd")
         scale = float(table.grad.abs().max())
         torch.testing.assert_close(g_w.double().cpu(), table.grad.t(), rtol=tol["rtol"], atol=tol["atol"] * max(1.0, scale))
         torch.testing.assert_close(g_b.double().cpu(), table.grad.sum(0), rtol=tol["rtol"], atol=tol["atol"] * 8 * max(1.0, scale))
         if dtype == ffi.PB_F32:
             gx2, parts2 = torch.empty_like(gx), torch.empty_like(parts)
             ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev),
-                                           ptr(gx2), ptr(parts2), ptr(bits), p_drop, st()), "agg_bwd")
+                                           ptr(gx2), ptr(q_buf), ptr(parts2), ptr(bits), p_drop, st()), "agg_bwd")
             assert torch.equal(gx, gx2) and torch.equal(parts, parts2)
 
 
