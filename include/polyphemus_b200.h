@@ -63,7 +63,9 @@ int pb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  *   bar_bits  u32 [n_bars,4]   bit t of word k = activation (track k, timestep t)
  *   node_ptr  i32 [n_bars+1]   exclusive scan of nodes per bar
  *   edge_ptr  i32 [n_bars+1]   exclusive scan of edges per bar (fake self-edge counted, data.py:173-176)
- *   totals    i64 [4]          {N, E, n_drum_nodes, max_nodes_per_bar}                                  */
+ *   totals    i64 [8]          {N, E, n_drum_nodes, n_bars, nodes per track-relation group g = 0..3}
+ *                              (group of a node = the relation of its incoming TRACK edges: its track, or 0 for
+ *                              the only node of a one-node bar, whose single in-edge is the fake self-edge)       */
 size_t pb_graph_workspace_bytes(int64_t n_bars);
 int pb_graph_count(uint8_t* s_tensor, int64_t n_bars, uint32_t* bar_bits, int32_t* node_ptr,
                    int32_t* edge_ptr, int64_t* totals, void* workspace, size_t workspace_bytes,
@@ -78,11 +80,12 @@ int pb_graph_count(uint8_t* s_tensor, int64_t n_bars, uint32_t* bar_bits, int32_
  *   is_drum       u8  [N]                                                 data.py:185
  *   bars          i64 [N]    bar index inside its sequence                data.py:202
  *   batch         i64 [N]    sequence index                               PyG add_batch
- *   node_track    u8  [N]    track of the node (internal helper, optional NULL)                          */
+ *   node_track    u8  [N]    track of the node (internal helper, optional NULL)
+ *   node_group    u8  [N]    track-relation group of the node (internal helper, optional NULL)           */
 int pb_graph_fill(const uint32_t* bar_bits, const int32_t* node_ptr, const int32_t* edge_ptr,
                   int64_t n_bars, int32_t bars_per_seq, int64_t* edge_index, int64_t n_edges,
                   uint8_t* edge_type, uint8_t* edge_dist, float* edge_attrs, float* node_features,
-                  uint8_t* is_drum, int64_t* bars, int64_t* batch, uint8_t* node_track,
+                  uint8_t* is_drum, int64_t* bars, int64_t* batch, uint8_t* node_track, uint8_t* node_group,
                   pb_stream_t stream);
 
 /* edge_attrs f32 [E,33] from (type, dist)  — data.py:179-182, materialised lazily. */
@@ -182,6 +185,12 @@ int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void
 int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
                           const void* wcat_lo, void* d_a, int64_t ldda, int64_t m, int32_t d, int32_t k,
                           int32_t dtype, pb_stream_t stream);
+/* Generic D[m,n] = A[m,k] @ B[n,k]^T (+ bias[n]) on the same tcgen05 kernel; out is f32 or bf16. Used for the
+ * nn.Linear layers adjacent to the path (chord encoder / decoder, model.py:322,525): forward and input gradient.
+ * Their weight gradient is pb_rgcn_gemm_bwd_weight (d = out features, k = in features). */
+int pb_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo, int64_t ldb,
+               const float* bias, void* out, int64_t ldo, int64_t m, int32_t n, int32_t k, int32_t dtype,
+               int32_t out_bf16, pb_stream_t stream);
 /* dWcat f32 [K,d] = A^T @ g (fixed-order split-K over the node dimension, deterministic). */
 size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k);
 int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,

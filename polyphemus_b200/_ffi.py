@@ -40,7 +40,7 @@ SIGNATURES = {
     "pb_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "pb_graph_workspace_bytes": (c_size_t, [c_int64]),
     "pb_graph_count": (c_int, [_P, c_int64, _P, _P, _P, _P, _P, c_size_t, _P]),
-    "pb_graph_fill": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pb_graph_fill": (c_int, [_P, _P, _P, c_int64, c_int32, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pb_edge_attrs_encode": (c_int, [_P, _P, c_int64, _P, _P]),
     "pb_edge_attrs_decode": (c_int, [_P, c_int64, _P, c_int64, c_int64, _P, _P, _P]),
     "pb_csr_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
@@ -55,6 +55,7 @@ SIGNATURES = {
     "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "pb_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
     "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
     "pb_rgcn_gemm_bwd_weight_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
     "pb_rgcn_gemm_bwd_weight": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32,
@@ -97,7 +98,7 @@ def lib() -> ctypes.CDLL:
 LAUNCHES = {
     "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
     "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
-    "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_rgcn_gemm_bwd_weight": 2,
+    "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,
 }

@@ -54,23 +54,25 @@ __global__ void __launch_bounds__(1024) edge_table_bwd_kernel(const float* __res
 // (chunk = 4 consecutive channels) — i.e. exactly the channels lane l of a warp owns in agg_fwd.
 static inline int keep_words(int d) { return ((d + 511) / 512) * 32; }   // u16 words per edge
 
-__global__ void dropout_bits_kernel(int64_t n_edges, int d, uint32_t thresh16, uint64_t seed, uint16_t* __restrict__ bits) {
+template <int G16>
+__global__ void __launch_bounds__(256) dropout_bits_kernel(int64_t n_edges, int d, uint32_t thresh16, uint64_t seed,
+                                                           uint16_t* __restrict__ bits) {
   const int nchunk = d >> 2;
-  const int g16 = (d + 511) / 512;
-  const int64_t total = n_edges * g16 * 32;
+  const int64_t total = n_edges * G16 * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int l = (int)(i & 31);
     const int64_t q = i >> 5;
-    const int jj = (int)(q % g16);
-    const int64_t e = q / g16;
+    const int jj = G16 == 1 ? 0 : (int)(q & (G16 - 1));
+    const uint32_t e = (uint32_t)(G16 == 1 ? q : q / G16);
     uint32_t w = 0;
 #pragma unroll
     for (int nib = 0; nib < 4; ++nib) {
       const int c = l + 32 * (4 * jj + nib);
       if (c < nchunk) {
-        bool k[4];
-        dropout_keep4(seed, (uint32_t)e, (uint32_t)c, thresh16, k);
-        w |= (uint32_t)(k[0] | (k[1] << 1) | (k[2] << 2) | (k[3] << 3)) << (4 * nib);
+        const uint64_t r = dropout_bits(seed, e, (uint32_t)c);
+        w |= ((uint32_t)((r & 0xFFFFu) >= thresh16) | ((uint32_t)(((r >> 16) & 0xFFFFu) >= thresh16) << 1) |
+              ((uint32_t)(((r >> 32) & 0xFFFFu) >= thresh16) << 2) | ((uint32_t)((r >> 48) >= thresh16) << 3))
+             << (4 * nib);
       }
     }
     bits[i] = (uint16_t)w;
@@ -367,8 +369,12 @@ extern "C" int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_
   if (n_edges == 0) return PB_OK;
   const int64_t total = n_edges * keep_words(d);
   const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-  dropout_bits_kernel<<<grid, 256, 0, as_stream(stream)>>>(n_edges, d, dropout_thresh(p_drop), seed,
-                                                           reinterpret_cast<uint16_t*>(keep_bits));
+  if (d <= 512)
+    dropout_bits_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(n_edges, d, dropout_thresh(p_drop), seed,
+                                                                reinterpret_cast<uint16_t*>(keep_bits));
+  else
+    dropout_bits_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(n_edges, d, dropout_thresh(p_drop), seed,
+                                                                reinterpret_cast<uint16_t*>(keep_bits));
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

@@ -164,7 +164,10 @@ struct Cfg {
   // ~2^-24 per MMA (measured: 1e-4 at K=3584 with three TF32 passes). The fp32-grade mode therefore hands the
   // accumulator to the CUDA cores every kPromoteKBlocks k-blocks (round-to-nearest adds in registers).
   static constexpr int kPromoteKBlocks = BF16 ? (1 << 30) : 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: per epilogue warp one 32-row x 32-column chunk, rows padded by 16 B (conflict-free both ways)
+  static constexpr int kStageRowF32 = 144, kStageRowBf16 = 80;
+  static constexpr int kEpiStageBytes = 32 * kStageRowF32;     // per warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4 * kEpiStageBytes;
 };
 
 constexpr int kGemmThreads = 192;
@@ -291,32 +294,51 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int buf = 0;
     uint32_t buf_phase = 0;
-    // one 32-column chunk of one output row: bias / convert / store
-    auto store32 = [&](const float* v, int64_t row, int col, int split) {
+    // One 32-row x 32-column chunk of the tile (thread = row after tcgen05.ld): bias / convert into a padded smem
+    // staging buffer of this warp, then store with lanes running along the row — every global store instruction
+    // writes whole 64/128-byte row segments instead of 32 scattered 16-byte pieces.
+    uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 + (warp - 2) * C::kEpiStageBytes;
+    auto store_chunk = [&](const float* v, int64_t row0, int col, int split) {
       if (p.out_bf16) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)split * p.split_stride +
-                           (size_t)row * p.ldd + col;
+        uint8_t* mine = stage + lane * C::kStageRowBf16;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (p.bias) { b0 = ldg4(p.bias + col + j); b1 = ldg4(p.bias + col + j + 4); }
           uint4 q;
-          q.x = pack_bf16x2(v[j + 0], v[j + 1]);
-          q.y = pack_bf16x2(v[j + 2], v[j + 3]);
-          q.z = pack_bf16x2(v[j + 4], v[j + 5]);
-          q.w = pack_bf16x2(v[j + 6], v[j + 7]);
-          *reinterpret_cast<uint4*>(o + j) = q;
+          q.x = pack_bf16x2(v[j + 0] + b0.x, v[j + 1] + b0.y);
+          q.y = pack_bf16x2(v[j + 2] + b0.z, v[j + 3] + b0.w);
+          q.z = pack_bf16x2(v[j + 4] + b1.x, v[j + 5] + b1.y);
+          q.w = pack_bf16x2(v[j + 6] + b1.z, v[j + 7] + b1.w);
+          *reinterpret_cast<uint4*>(mine + 2 * j) = q;
+        }
+        __syncwarp();
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)split * p.split_stride + col;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {            // 8 rows x 64 B per instruction
+          const int r = i * 8 + (lane >> 2), c16 = lane & 3;
+          const uint4 q = *reinterpret_cast<const uint4*>(stage + r * C::kStageRowBf16 + c16 * 16);
+          if (row0 + r < p.m) *reinterpret_cast<uint4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 8) = q;
         }
       } else {
-        float* o = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + (size_t)row * p.ldd + col;
+        uint8_t* mine = stage + lane * C::kStageRowF32;
+        float4 bq[8];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 q = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.bias) {
-            const float4 b = ldg4(p.bias + col + j);
-            q.x += b.x; q.y += b.y; q.z += b.z; q.w += b.w;
-          }
-          *reinterpret_cast<float4*>(o + j) = q;
+        for (int j = 0; j < 8; ++j) bq[j] = p.bias ? ldg4(p.bias + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(mine + 16 * j) = make_float4(v[4 * j] + bq[j].x, v[4 * j + 1] + bq[j].y,
+                                                                   v[4 * j + 2] + bq[j].z, v[4 * j + 3] + bq[j].w);
+        __syncwarp();
+        float* o = reinterpret_cast<float*>(p.out) + (size_t)split * p.split_stride + col;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {            // 4 rows x 128 B per instruction
+          const int r = i * 4 + (lane >> 3), c16 = lane & 7;
+          const float4 q = *reinterpret_cast<const float4*>(stage + r * C::kStageRowF32 + c16 * 16);
+          if (row0 + r < p.m) *reinterpret_cast<float4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 4) = q;
         }
       }
+      __syncwarp();   // staging buffer is reused by the next chunk
     };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int split = t / tiles_mn, mn = t - split * tiles_mn;
@@ -324,8 +346,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const int n0 = (mn % p.num_n_tiles) * C::BN;
       const int kb0 = split * p.k_blocks_per_split;
       const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
-      const int64_t row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.m;
+      const int64_t row0 = m0 + quad * 32;      // first row of this warp's TMEM lane quadrant
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
       if constexpr (BF16) {
         // single accumulation: stream TMEM -> registers -> global
@@ -335,8 +356,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         for (int c0 = 0; c0 < C::BN; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(lane_base + (uint32_t)(buf * C::BN + c0), v);
-          if (row_ok && n0 + c0 < p.n)   // n is a multiple of 32 (host check): whole chunk in range
-            store32(reinterpret_cast<const float*>(v), row, n0 + c0, split);
+          if (row0 < p.m && n0 + c0 < p.n)   // warp-uniform; n is a multiple of 32 (host check): whole chunk in range
+            store_chunk(reinterpret_cast<const float*>(v), row0, n0 + c0, split);
         }
         tc_fence_before();
         __syncwarp();
@@ -367,7 +388,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
 #pragma unroll
         for (int c0 = 0; c0 < C::BN; c0 += 32)
-          if (row_ok && n0 + c0 < p.n) store32(acc + c0, row, n0 + c0, split);
+          if (row0 < p.m && n0 + c0 < p.n) store_chunk(acc + c0, row0, n0 + c0, split);
       }
     }
   }
@@ -539,7 +560,7 @@ static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n,
 
 static int check_gemm_dims(int64_t m, int d, int k, int dtype, const char* who) {
   PB_REQUIRE(m > 0 && m < ((int64_t)1 << 31), "%s: m out of range", who);
-  PB_REQUIRE(d >= 64 && d % 64 == 0 && d <= 1024, "%s: d=%d must be a multiple of 64 in [64, 1024]", who, d);
+  PB_REQUIRE(d >= 64 && d % 64 == 0, "%s: d=%d must be a multiple of 64", who, d);
   PB_REQUIRE(k >= 64 && k % 64 == 0, "%s: k=%d must be a multiple of 64", who, k);
   PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "%s: bad dtype", who);
   return PB_OK;
@@ -571,6 +592,24 @@ extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda,
   cudaStream_t st = as_stream(stream);
   rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st)
                         : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st);
+  return rc < 0 ? rc : PB_OK;
+}
+
+// Generic D[m,n] = A[m,k] . B[n,k]^T (+ bias[n]) on the same kernel: any nn.Linear forward / input gradient.
+extern "C" int pb_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi, const void* b_lo,
+                          int64_t ldb, const float* bias, void* out, int64_t ldo, int64_t m, int32_t n, int32_t k,
+                          int32_t dtype, int32_t out_bf16, pb_stream_t stream) {
+  int rc = check_gemm_dims(m, n, k, dtype, "pb_gemm_nt");
+  if (rc) return rc;
+  PB_REQUIRE(a_hi && b_hi && out, "pb_gemm_nt: null pointer");
+  PB_REQUIRE(dtype == PB_BF16 || (a_lo && b_lo), "pb_gemm_nt: PB_F32 needs lo operands");
+  PB_REQUIRE(lda >= k && lda % 8 == 0 && ldb >= k && ldb % 8 == 0 && ldo >= n && ldo % 8 == 0,
+             "pb_gemm_nt: bad leading dimension");
+  Operand a{a_hi, a_lo, m, k, lda, false};
+  Operand b{b_hi, b_lo, n, k, ldb, false};
+  cudaStream_t st = as_stream(stream);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, n, k, out, ldo, out_bf16 != 0, bias, 1, 0, st)
+                        : launch_gemm<false>(a, b, m, n, k, out, ldo, out_bf16 != 0, bias, 1, 0, st);
   return rc < 0 ? rc : PB_OK;
 }
 

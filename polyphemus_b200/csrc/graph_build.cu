@@ -36,6 +36,15 @@ __global__ void __launch_bounds__(kBarsPerBlock * 32) graph_count_kernel(uint8_t
     node_cnt[bar] = p.n_nodes;
     edge_cnt[bar] = p.n_edges;
     atomicAdd(totals + 2, (unsigned long long)p.n[0]);  // drum nodes (integer add: deterministic)
+    // nodes per track-relation group (see node_group in pb_graph_fill): the only node of a one-node bar receives
+    // the fake self-edge of type 0 (data.py:173-176), every other node receives track edges of its own track
+    if (p.n_nodes == 1) {
+      atomicAdd(totals + 4, 1ull);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (p.n[k]) atomicAdd(totals + 4 + k, (unsigned long long)p.n[k]);
+    }
   }
 }
 
@@ -54,7 +63,7 @@ __global__ void __launch_bounds__(kBarsPerBlock * 32)
                       uint8_t* __restrict__ edge_type, uint8_t* __restrict__ edge_dist,
                       float* __restrict__ edge_attrs, float* __restrict__ node_features,
                       uint8_t* __restrict__ is_drum, long long* __restrict__ bars, long long* __restrict__ batch,
-                      uint8_t* __restrict__ node_track) {
+                      uint8_t* __restrict__ node_track, uint8_t* __restrict__ node_group) {
   const int lane = threadIdx.x & 31;
   const int64_t bar = (int64_t)blockIdx.x * kBarsPerBlock + (threadIdx.x >> 5);
   if (bar >= n_bars) return;
@@ -87,6 +96,7 @@ __global__ void __launch_bounds__(kBarsPerBlock * 32)
     bars[v] = bar_in_seq;
     batch[v] = seq;
     if (node_track) node_track[v] = (uint8_t)k;
+    if (node_group) node_group[v] = p.n_nodes == 1 ? (uint8_t)0 : (uint8_t)k;
   }
 
   // optional dense edge_attrs rows (data.py:179-182): the warp writes each 33-float row cooperatively
@@ -158,7 +168,7 @@ extern "C" int pb_graph_count(uint8_t* s_tensor, int64_t n_bars, uint32_t* bar_b
   void* scan_ws0 = ws;
   ws += scan_workspace_bytes(n_bars);
   void* scan_ws1 = ws;
-  PB_CUDA(cudaMemsetAsync(totals, 0, 4 * sizeof(int64_t), st));
+  PB_CUDA(cudaMemsetAsync(totals, 0, 8 * sizeof(int64_t), st));
   const unsigned grid = (unsigned)((n_bars + kBarsPerBlock - 1) / kBarsPerBlock);
   graph_count_kernel<<<grid, kBarsPerBlock * 32, 0, st>>>(s_tensor, n_bars, bar_bits, node_cnt, edge_cnt,
                                                           reinterpret_cast<unsigned long long*>(totals));
@@ -176,7 +186,7 @@ extern "C" int pb_graph_fill(const uint32_t* bar_bits, const int32_t* node_ptr, 
                              int64_t n_bars, int32_t bars_per_seq, int64_t* edge_index, int64_t n_edges,
                              uint8_t* edge_type, uint8_t* edge_dist, float* edge_attrs, float* node_features,
                              uint8_t* is_drum, int64_t* bars, int64_t* batch, uint8_t* node_track,
-                             pb_stream_t stream) {
+                             uint8_t* node_group, pb_stream_t stream) {
   PB_REQUIRE(bar_bits && node_ptr && edge_ptr && edge_index && edge_type && edge_dist && node_features &&
                  is_drum && bars && batch,
              "pb_graph_fill: null pointer");
@@ -186,7 +196,7 @@ extern "C" int pb_graph_fill(const uint32_t* bar_bits, const int32_t* node_ptr, 
   graph_fill_kernel<<<grid, kBarsPerBlock * 32, 0, as_stream(stream)>>>(
       bar_bits, node_ptr, edge_ptr, n_bars, bars_per_seq, reinterpret_cast<long long*>(edge_index),
       reinterpret_cast<long long*>(edge_index) + n_edges, edge_type, edge_dist, edge_attrs, node_features,
-      is_drum, reinterpret_cast<long long*>(bars), reinterpret_cast<long long*>(batch), node_track);
+      is_drum, reinterpret_cast<long long*>(bars), reinterpret_cast<long long*>(batch), node_track, node_group);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

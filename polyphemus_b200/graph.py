@@ -147,12 +147,12 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
         bar_bits = torch.empty((total_bars, 4), dtype=torch.int32, device=dev)
         node_ptr = torch.empty(total_bars + 1, dtype=torch.int32, device=dev)
         edge_ptr = torch.empty(total_bars + 1, dtype=torch.int32, device=dev)
-        totals = torch.empty(4, dtype=torch.int64, device=dev)
+        totals = torch.empty(8, dtype=torch.int64, device=dev)
         ws_bytes = lib.pb_graph_workspace_bytes(total_bars)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _ffi.call("pb_graph_count", s_u8.data_ptr(), total_bars, bar_bits.data_ptr(), node_ptr.data_ptr(),
                   edge_ptr.data_ptr(), totals.data_ptr(), ws.data_ptr(), ws_bytes, st)
-        n, e, n_drum, _ = (int(v) for v in totals.tolist())          # the one host sync
+        n, e, n_drum, _, *group_counts = (int(v) for v in totals.tolist())          # the one host sync
         edge_index = torch.empty((2, e), dtype=torch.int64, device=dev)
         edge_type = torch.empty(e, dtype=torch.uint8, device=dev)
         edge_dist = torch.empty(e, dtype=torch.uint8, device=dev)
@@ -162,15 +162,17 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
         bars = torch.empty(n, dtype=torch.int64, device=dev)
         batch = torch.empty(n, dtype=torch.int64, device=dev)
         node_track = torch.empty(n, dtype=torch.uint8, device=dev)
+        node_group = torch.empty(n, dtype=torch.uint8, device=dev)
         _ffi.call("pb_graph_fill", bar_bits.data_ptr(), node_ptr.data_ptr(), edge_ptr.data_ptr(), total_bars, n_bars,
                   edge_index.data_ptr(), e, edge_type.data_ptr(), edge_dist.data_ptr(), _ffi.ptr(edge_attrs),
                   node_features.data_ptr(), is_drum.data_ptr(), bars.data_ptr(), batch.data_ptr(),
-                  node_track.data_ptr(), st)
+                  node_track.data_ptr(), node_group.data_ptr(), st)
     if write_back is not None:
         write_back.copy_(s_u8.view(write_back.dtype).reshape(write_back.shape))
     g = Graph(edge_index=edge_index, edge_type=edge_type, edge_dist=edge_dist, node_features=node_features,
               is_drum=is_drum, bars=bars, batch=batch, num_nodes=n, num_edges=e, num_graphs=bsz, n_bars=n_bars,
-              n_drum=n_drum, node_track=node_track, bar_ptr=node_ptr)
+              n_drum=n_drum, node_track=node_track, node_group=node_group, group_counts=group_counts,
+              bar_ptr=node_ptr)
     if edge_attrs is not None:
         g._edge_attrs = edge_attrs
     return g

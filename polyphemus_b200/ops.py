@@ -251,6 +251,82 @@ def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, b
     return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg)
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# Dense layers adjacent to the path (chord encoder / decoder) on the same tcgen05 GEMM.
+def _tf32_split(t: torch.Tensor):
+    t = t.contiguous()                                                        # lo must share hi's row-major layout
+    hi = (t.view(torch.int32) & -8192).view(torch.float32)                    # top 19 bits: a valid TF32 value
+    return hi, t - hi
+
+
+def _as_operand(t: torch.Tensor, dtype: int):
+    if dtype == _ffi.PB_BF16:
+        return (t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)).contiguous(), None
+    return _tf32_split(t.float())
+
+
+class TensorCoreLinearFn(torch.autograd.Function):
+    """y = x @ weight.T + bias with pb_gemm_nt (forward, input gradient) and the deterministic split-K
+    pb_rgcn_gemm_bwd_weight (weight gradient). Precision follows the path's mode (bf16, or TF32x3 = fp32-grade)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, dtype: int, out_bf16: bool):
+        m, k = x.shape
+        n = weight.shape[0]
+        dev = x.device
+        x_hi, x_lo = _as_operand(x, dtype)
+        w_hi, w_lo = _as_operand(weight, dtype)
+        out_bf16 = bool(out_bf16 and dtype == _ffi.PB_BF16)
+        out = torch.empty((m, n), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
+        bias_f = None if bias is None else bias.float().contiguous()
+        with torch.cuda.device(dev):
+            _call("pb_gemm_nt", x_hi.data_ptr(), _ffi.ptr(x_lo), k, w_hi.data_ptr(), _ffi.ptr(w_lo), k,
+                  _ffi.ptr(bias_f), out.data_ptr(), n, m, n, k, dtype, int(out_bf16), _ffi.stream())
+        ctx.save_for_backward(x_hi, x_lo, weight)
+        ctx.dtype, ctx.has_bias, ctx.x_dtype = dtype, bias is not None, x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x_hi, x_lo, weight = ctx.saved_tensors
+        dtype = ctx.dtype
+        m, k = x_hi.shape
+        n = weight.shape[0]
+        dev = g.device
+        g_hi, g_lo = _as_operand(g, dtype)
+        lib = _ffi.lib()
+        with torch.cuda.device(dev):
+            st = _ffi.stream()
+            dx = None
+            if ctx.needs_input_grad[0]:
+                wt_hi, wt_lo = _as_operand(weight.t(), dtype)                   # [k, n], contraction dim contiguous
+                dx_bf16 = dtype == _ffi.PB_BF16 and ctx.x_dtype == torch.bfloat16
+                dx = torch.empty((m, k), dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev)
+                _call("pb_gemm_nt", g_hi.data_ptr(), _ffi.ptr(g_lo), n, wt_hi.data_ptr(), _ffi.ptr(wt_lo), n, None,
+                      dx.data_ptr(), k, m, k, n, dtype, int(dx_bf16), st)
+            dw = None
+            if ctx.needs_input_grad[1]:
+                dw = torch.empty((n, k), dtype=torch.float32, device=dev)
+                ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(m, k, n)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                # dW[n, k] = g^T @ x: the split-K kernel contracts over the rows of its two [m, .] operands
+                _call("pb_rgcn_gemm_bwd_weight", g_hi.data_ptr(), _ffi.ptr(g_lo), n, x_hi.data_ptr(), _ffi.ptr(x_lo), k,
+                      dw.data_ptr(), m, k, n, dtype, ws.data_ptr(), ws_bytes, st)
+        db = g.sum(0, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], out_bf16: bool = False,
+              precision: Optional[str] = None) -> torch.Tensor:
+    """nn.Linear on the tcgen05 GEMM for 2-D CUDA inputs whose sizes are multiples of 64; plain F.linear
+    otherwise (CPU construction / odd shapes are outside the accelerated path, not a fallback of it)."""
+    n, k = weight.shape
+    if not (x.is_cuda and x.dim() == 2 and n % 64 == 0 and k % 64 == 0):
+        return torch.nn.functional.linear(x, weight, bias)
+    dtype = _PRECISIONS[precision or _default_precision]
+    return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
+
+
 def dropout_keep_mask(n_edges: int, d: int, p_drop: float, seed: int, device) -> torch.Tensor:
     """The keep-mask pb_agg_fwd/bwd use for (seed, p): bool [E, d], indexed by edge_index column."""
     keep = torch.empty((n_edges, d), dtype=torch.uint8, device=device)

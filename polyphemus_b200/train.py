@@ -55,11 +55,10 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
 
 def _masked_ce(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
     """nn.CrossEntropyLoss(ignore_index=...) (training.py:100-101): mean over the non-ignored rows of
-    logsumexp(logits) - logits[target]. Written out because the library's nll_loss reduction runs in a single
-    block and costs milliseconds on 2M rows."""
+    -log_softmax(logits)[target]. Written out because the library's nll_loss reduction runs in a single block and
+    costs milliseconds on 2M rows (the fused log_softmax kernel is fine)."""
     keep = target != ignore_index
-    picked = logits.gather(1, target.unsqueeze(1)).squeeze(1)
-    nll = torch.logsumexp(logits, dim=1) - picked
+    nll = -F.log_softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
     return (nll * keep).sum() / keep.sum()
 
 
@@ -164,6 +163,7 @@ class GradAllReducer:
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._handles = []
+        self.sync = True             # False: accumulate locally only (gradient accumulation / single-rank checks)
         if self.world > 1:
             for p in self.params:
                 p.register_post_accumulate_grad_hook(self._hook)
@@ -176,6 +176,8 @@ class GradAllReducer:
         self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _hook(self, p) -> None:
+        if not self.sync:
+            return
         b = self._bucket_of[p]
         self._ready[b] += 1
         if self._ready[b] == self.buckets[b][2]:
@@ -188,7 +190,7 @@ class GradAllReducer:
 
     def finish(self) -> None:
         """Flush incomplete buckets, wait for all reductions, average."""
-        if self.world == 1:
+        if self.world == 1 or not self.sync:
             return
         for b in range(len(self.buckets)):
             self._launch(b)

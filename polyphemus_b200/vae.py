@@ -22,6 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from . import ops
 from .conv import GCN, _reset
 from .graph import Graph, graphs_from_tensor
 
@@ -181,9 +182,12 @@ class ContentEncoder(nn.Module):
         if k == 0:
             return torch.zeros((0, self.d), dtype=torch.float32, device=ids.device)
         p_ids, d_ids = ids[..., 0].long(), ids[..., 1].long()
-        pitch = F.embedding(p_ids, self._bn_table(pitch_emb, pitch_bn, p_ids, self.training))
-        dur = F.embedding(d_ids, self._bn_table(self.dur_emb, self.bn_dur, d_ids, self.training))
-        chord = self.chord_encoder(torch.cat((pitch, dur), dim=-1).view(k, t * self.d))
+        p_tab = self._bn_table(pitch_emb, pitch_bn, p_ids, self.training)
+        d_tab = self._bn_table(self.dur_emb, self.bn_dur, d_ids, self.training)
+        if ops.get_precision() == "bf16":          # gather straight into the GEMM's operand dtype
+            p_tab, d_tab = p_tab.to(torch.bfloat16), d_tab.to(torch.bfloat16)
+        tokens = torch.cat((F.embedding(p_ids, p_tab), F.embedding(d_ids, d_tab)), dim=-1).view(k, t * self.d)
+        chord = ops.tc_linear(tokens, self.chord_encoder.weight, self.chord_encoder.bias)
         return self.dropout_layer(F.relu(chord))
 
     def forward(self, graph):
@@ -287,8 +291,11 @@ class ContentDecoder(nn.Module):
         t = MAX_SIMU_TOKENS - 1
         w = self.chord_decoder.weight.view(t, 2, half, d)
         b = self.chord_decoder.bias.view(t, 2, half)
-        h_pitch = self.dropout_layer(F.linear(h, w[:, 0].reshape(t * half, d), b[:, 0].reshape(-1))).view(-1, t, half)
-        h_dur = self.dropout_layer(F.linear(h, w[:, 1].reshape(t * half, d), b[:, 1].reshape(-1))).view(-1, t, half)
+        bf16 = ops.get_precision() == "bf16"
+        h_pitch = ops.tc_linear(h, w[:, 0].reshape(t * half, d), b[:, 0].reshape(-1), out_bf16=bf16)
+        h_dur = ops.tc_linear(h, w[:, 1].reshape(t * half, d), b[:, 1].reshape(-1), out_bf16=bf16)
+        h_pitch = self.dropout_layer(h_pitch).view(-1, t, half)
+        h_dur = self.dropout_layer(h_dur).view(-1, t, half)
         # both pitch heads on every node, then select per node: no compaction, no host sync
         is_drum = s.is_drum.view(-1, 1, 1)
         pitch = torch.where(is_drum, self.drums_pitch_emb(h_pitch), self.non_drums_pitch_emb(h_pitch))

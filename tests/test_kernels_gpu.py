@@ -369,3 +369,29 @@ def test_dropout_mask_matches_host_definition(cuda):
     # neighbouring channels / edges are uncorrelated
     b = big.float() - big.float().mean()
     assert abs(float((b[:, :-1] * b[:, 1:]).mean())) < 1e-3 and abs(float((b[:-1] * b[1:]).mean())) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("m,k,n", [(300, 512, 3840), (1000, 7680, 512), (70, 64, 64)])
+def test_tensor_core_linear(cuda, precision, m, k, n):
+    """ops.tc_linear (chord encoder / decoder shapes, model.py:322,525) against fp64 F.linear, forward + gradients."""
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(m + k + n)
+    x = torch.randn(m, k, generator=gen).to(cuda).requires_grad_(True)
+    w = (torch.randn(n, k, generator=gen) / np.sqrt(k)).to(cuda).requires_grad_(True)
+    b = torch.randn(n, generator=gen).to(cuda).requires_grad_(True)
+    gy = torch.randn(m, n, generator=gen).to(cuda)
+    y = ops.tc_linear(x, w, b, precision=precision)
+    y.backward(gy)
+    x64, w64, b64 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    y64 = torch.nn.functional.linear(x64, w64, b64)
+    y64.backward(gy.double())
+    if precision == "fp32":
+        tol = lambda ref: dict(rtol=1e-4, atol=1e-5 * max(1.0, float(ref.abs().max())))
+    else:
+        tol = lambda ref: dict(rtol=3e-2, atol=3e-2 * float(ref.abs().max()))
+    torch.testing.assert_close(y.double(), y64, **tol(y64))
+    torch.testing.assert_close(x.grad.double(), x64.grad, **tol(x64.grad))
+    torch.testing.assert_close(w.grad.double(), w64.grad, **tol(w64.grad))
+    torch.testing.assert_close(b.grad.double(), b64.grad, **tol(b64.grad))
