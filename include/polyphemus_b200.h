@@ -48,6 +48,16 @@ enum pb_dtype { PB_F32 = 0, PB_BF16 = 1 };
 
 enum { PB_N_TRACKS = 4, PB_N_TIMESTEPS = 32, PB_N_DISTS = 32, PB_N_RELATIONS = 6, PB_DIST_ITEMS = 1184 };
 
+/* Row groups of the structured node layout: nodes sorted by the relation of their incoming TRACK
+ * edges, every group padded with zero rows to a multiple of 128 so that a GEMM tile never mixes two groups.
+ * `count[g]` real rows start at padded row `start[g]`. NULL wherever accepted = one group {0, m}. */
+typedef struct pb_groups {
+  int32_t n_groups; /* <= 4 */
+  int32_t reserved;
+  int64_t start[4];
+  int64_t count[4];
+} pb_groups_t;
+
 int pb_version(void);
 const char* pb_last_error(void);
 /* Host-side query: SM count and compute capability of the current device. */
@@ -177,14 +187,18 @@ int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uin
 int pb_weight_prep(const float* weight, const float* root, int32_t n_relations, int32_t d, int32_t dtype,
                    void* wcat_hi, void* wcat_lo, void* wcat_t_hi, void* wcat_t_lo, pb_stream_t stream);
 /* out f32 [M, d] = A[M,K] @ Wcat[K,d] + bias (bias may be NULL).  wcat_t_* is [d, K] (K contiguous). */
+/* Structured form (groups != NULL): A is [M, 4d] = [H_track | H_onset | H_next | x] with the rows in group order;
+ * a row of group g contracts against [weight[g]; weight[4]; weight[5]; root] — the same result with 4/7 of the
+ * flops, because a node only ever receives TRACK edges of one relation. k is then 4*d while the weight operands
+ * keep their full (R+1)*d extent. */
 int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
                      const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
-                     int32_t k, int32_t dtype, pb_stream_t stream);
+                     int32_t k, const pb_groups_t* groups, int32_t dtype, pb_stream_t stream);
 /* dA [M,K] = g[M,d] @ Wcat^T.  g_* is the GEMM-operand copy of the output gradient (bf16, or f32 hi/lo);
  * dA is bf16 (PB_BF16) or f32 (PB_F32). */
 int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
                           const void* wcat_lo, void* d_a, int64_t ldda, int64_t m, int32_t d, int32_t k,
-                          int32_t dtype, pb_stream_t stream);
+                          const pb_groups_t* groups, int32_t dtype, pb_stream_t stream);
 /* Generic D[m,n] = A[m,k] @ B[n,k]^T (+ bias[n]) on the same tcgen05 kernel; out is f32 or bf16. Used for the
  * nn.Linear layers adjacent to the path (chord encoder / decoder, model.py:322,525): forward and input gradient.
  * Their weight gradient is pb_rgcn_gemm_bwd_weight (d = out features, k = in features). */
@@ -193,9 +207,12 @@ int pb_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi
                int32_t out_bf16, pb_stream_t stream);
 /* dWcat f32 [K,d] = A^T @ g (fixed-order split-K over the node dimension, deterministic). */
 size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k);
+/* Structured form (groups != NULL, k == 4d): d_wcat is the full [(R+1)d, d]; the split boundaries follow the row
+ * groups, the track block of the partials is reduced per group into weight[g], the other blocks over all rows. */
 int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
                             const void* g_lo, int64_t ldg, float* d_wcat, int64_t m, int32_t d, int32_t k,
-                            int32_t dtype, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+                            const pb_groups_t* groups, int32_t dtype, void* workspace, size_t workspace_bytes,
+                            pb_stream_t stream);
 /* Plain-fp32 CUDA-core contraction D[M,N] = A[M,K] @ B[K,N] (+bias) used by the tests to cross-check the
  * tensor-core kernels on device; not on the product path. */
 int pb_gemm_f32_check(const float* a, int64_t lda, const float* b, int64_t ldb, const float* bias, float* d_out,
@@ -211,22 +228,23 @@ int pb_gemm_f32_check(const float* a, int64_t lda, const float* b, int64_t ldb, 
 size_t pb_bn_workspace_bytes(int64_t m, int32_t d);
 /* bn_coef f32 [3,d] = {mean, scale = gamma*rstd, beta}; save_mean_rstd f32 [2,d];
  * running_mean/var updated in place when not NULL. */
-int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const float* gamma, const float* beta,
-                float eps, float momentum, float* running_mean, float* running_var, float* save_mean_rstd,
-                float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups, const float* gamma,
+                const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                float* save_mean_rstd, float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream);
 int pb_bn_prepare_eval(const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, int32_t d, float* bn_coef,
                        pb_stream_t stream);
 /* y = x_res + relu((out-mean)*scale + beta)   (x_res may be NULL: y = relu(...)); apply_relu=0 skips the ReLU */
 int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef,
-                       float* y, int64_t m, int32_t d, int32_t apply_relu, pb_stream_t stream);
+                       float* y, int64_t m, int32_t d, const pb_groups_t* groups, int32_t apply_relu,
+                       pb_stream_t stream);
 /* Backward of y = x + relu(bn(out)) wrt out (training statistics):
  *   g_out f32 [m,d] (+ GEMM-operand copies g_hi/g_lo in `dtype`), g_gamma, g_beta, g_bias(=colsum g_out).
  *   The residual branch gradient is gy itself (consumed by pb_agg_bwd as gy_res). */
 int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
                        const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
-                       int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma, float* g_beta,
-                       float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+                       const pb_groups_t* groups, int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma,
+                       float* g_beta, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
 /* Operand conversion for a plain GCL (no BN): g f32 [m,d] -> g_hi/g_lo in `dtype`, and g_bias = colsum. */
 int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d, int32_t dtype, void* g_hi, void* g_lo,
                  int64_t ldg, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);

@@ -32,6 +32,10 @@ class CsrStruct(Structure):
     ]
 
 
+class GroupsStruct(Structure):
+    _fields_ = [("n_groups", c_int32), ("reserved", c_int32), ("start", c_int64 * 4), ("count", c_int64 * 4)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/polyphemus_b200.h (tests check this)
 _P = c_void_p
 SIGNATURES = {
@@ -54,20 +58,23 @@ SIGNATURES = {
     "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, _P]),
     "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
-    "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
+                                 POINTER(GroupsStruct), c_int32, _P]),
     "pb_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
-    "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P]),
+    "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
+                                      POINTER(GroupsStruct), c_int32, _P]),
     "pb_rgcn_gemm_bwd_weight_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
-    "pb_rgcn_gemm_bwd_weight": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32,
-                                        _P, c_size_t, _P]),
+    "pb_rgcn_gemm_bwd_weight": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32,
+                                        POINTER(GroupsStruct), c_int32, _P, c_size_t, _P]),
     "pb_gemm_f32_check": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32,
                                   c_int32, _P]),
     "pb_bn_workspace_bytes": (c_size_t, [c_int64, c_int32]),
-    "pb_bn_stats": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pb_bn_stats": (c_int, [_P, c_int64, c_int64, c_int32, POINTER(GroupsStruct), _P, _P, c_float, c_float, _P, _P, _P, _P,
+                            _P, c_size_t, _P]),
     "pb_bn_prepare_eval": (c_int, [_P, _P, _P, _P, c_float, c_int32, _P, _P]),
-    "pb_bn_relu_res_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
-    "pb_bn_relu_res_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P,
-                                   _P, _P, c_size_t, _P]),
+    "pb_bn_relu_res_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, POINTER(GroupsStruct), c_int32, _P]),
+    "pb_bn_relu_res_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int32, POINTER(GroupsStruct), c_int32, _P, _P,
+                                   c_int64, _P, _P, _P, _P, c_size_t, _P]),
     "pb_grad_prep": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P, c_size_t, _P]),
 }
 
@@ -128,14 +135,16 @@ class EventProfiler:
 profiler = EventProfiler()
 
 
-def call(name: str, *args, meta=None) -> None:
+def call(name: str, *args, tag=None) -> None:
+    """Invoke an ABI entry point. `tag` only labels the profiler record (e.g. "linear" for the dense layers next to
+    the path, so that they are not counted as message-passing launches)."""
     fn = getattr(lib(), name)
     if profiler.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        profiler.records.append((name, e0, e1, meta))
+        profiler.records.append((name if tag is None else f"{name}:{tag}", e0, e1, None))
     else:
         rc = fn(*args)
     check(rc, name)

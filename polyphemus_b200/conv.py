@@ -94,7 +94,7 @@ class GCL(nn.Module):
         return self._plan
 
     def forward(self, x, edge_index=None, edge_type=None, edge_attr=None, *, plan: Optional[CsrPlan] = None,
-                bn: Optional[nn.BatchNorm1d] = None):
+                bn: Optional[nn.BatchNorm1d] = None, struct=None):
         """``bn`` fuses BatchNorm + ReLU + residual of the enclosing GCN layer (model.py:202-206)."""
         if isinstance(x, tuple) or x is None or x.dtype == torch.long:
             raise NotImplementedError("bipartite / index-valued node inputs are not part of the Polyphemus path")
@@ -114,7 +114,7 @@ class GCL(nn.Module):
             training = self.training
         return ops.rgc_layer(x, self.weight, self.root, self.bias, nn_w, nn_b, plan, batch_norm=bn is not None,
                              training=training, p_drop=self.dropout if self.training else 0.0,
-                             precision=self.precision, **kw)
+                             precision=self.precision, struct=struct, **kw)
 
     def extra_repr(self) -> str:
         return f"{self.in_channels}, {self.out_channels}, num_relations={self.num_relations}, dropout={self.dropout}"
@@ -151,6 +151,14 @@ class GCN(nn.Module):
 
     def forward(self, data):
         x = data.x
+        st = data.structured if isinstance(data, Graph) and ops.structured_enabled() else None
+        if st is not None and self.batch_norm and self.p == 0 and x.size(1) % 256 == 0 and x.is_cuda:
+            # structured layout: nodes sorted by track relation, groups padded to the GEMM tile (zero rows), the
+            # whole stack runs on [Np, d]; one gather in, one gather out
+            xp = torch.zeros((st.n_padded, x.size(1)), dtype=x.dtype, device=x.device).index_copy(0, st.pos, x)
+            for i, layer in enumerate(self.layers):
+                xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st)
+            return xp.index_select(0, st.pos)
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):
             residual = x

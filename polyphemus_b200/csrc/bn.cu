@@ -8,9 +8,52 @@
 //
 // bn_coef layout (f32 [3,d]): row 0 = mean, row 1 = scale (= gamma * rstd), row 2 = beta
 //   y = x_res + relu((out - mean) * scale + beta)
+#include <string.h>
+
 #include "common.cuh"
 
 namespace pb {
+
+// Row groups of the structured (track-relation-sorted, 128-row padded) node layout: `count[g]` valid rows starting
+// at padded row `start[g]`; the rows in between are zero padding that takes no part in the statistics. A plain
+// [m, d] matrix is one group {0, m}.
+struct RowMap {
+  int n;
+  long long total;     // valid rows (= cum[n]); separate field so that kernels never index the arrays dynamically
+  long long cum[5];    // cum[g] = valid rows before group g
+  long long start[4];
+  __device__ __forceinline__ long long padded(long long r) const {   // compact valid index -> padded row
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < n && r < cum[g + 1]) return start[g] + (r - cum[g]);
+    return r;
+  }
+  __device__ __forceinline__ bool valid(long long p) const {         // is padded row p a real node?
+    bool ok = false;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ok = ok || (g < n && p >= start[g] && p < start[g] + (cum[g + 1] - cum[g]));
+    return ok;
+  }
+};
+
+static RowMap make_rowmap(const pb_groups_t* groups, int64_t m) {
+  RowMap rm;
+  memset(&rm, 0, sizeof(rm));
+  if (!groups || groups->n_groups <= 0) {
+    rm.n = 1;
+    rm.cum[1] = rm.cum[2] = rm.cum[3] = rm.cum[4] = m;
+    rm.total = m;
+    return rm;
+  }
+  rm.n = groups->n_groups;
+  for (int g = 0; g < 4; ++g) {
+    rm.start[g] = g < rm.n ? groups->start[g] : 0;
+    rm.cum[g + 1] = rm.cum[g] + (g < rm.n ? groups->count[g] : 0);
+  }
+  rm.total = rm.cum[4];
+  return rm;
+}
+static inline int64_t valid_rows(const RowMap& rm) { return rm.total; }
 
 constexpr int kColThreads = 256;
 constexpr int kColMaxCtas = 148 * 4;
@@ -23,7 +66,8 @@ static inline int col_ctas(int64_t m) {
 // Each CTA reduces a contiguous row range for every column; thread = (row group, float4 column chunk).
 // partials: [gridDim.x][NV][d]
 template <int NV, class Load>
-__device__ __forceinline__ void column_partials(int64_t m, int d, float* __restrict__ partials, Load load) {
+__device__ __forceinline__ void column_partials(const RowMap& rm, int d, float* __restrict__ partials, Load load) {
+  const int64_t m = rm.total;   // valid rows; the loader receives padded row indices
   extern __shared__ float red[];  // [NV][nrg][d]
   const int nchunk = d >> 2;
   const int nrg = kColThreads / nchunk;
@@ -35,11 +79,21 @@ __device__ __forceinline__ void column_partials(int64_t m, int d, float* __restr
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (rg < nrg) {
-    for (int64_t r = r0 + rg; r < r1; r += nrg) {
-      float4 v[NV];
-      load(r, c, v);
+    // walk the CTA's compact row range group by group: inside a group compact and padded rows differ by a constant
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+    for (int g = 0; g < 4; ++g) {   // groups beyond rm.n are empty (cum[g] == cum[g+1])
+      const int64_t lo = r0 > rm.cum[g] ? r0 : rm.cum[g];
+      const int64_t hi = r1 < rm.cum[g + 1] ? r1 : rm.cum[g + 1];
+      const int64_t shift = rm.start[g] - rm.cum[g];
+      // keep the row-group phase of the plain loop: thread row-group rg owns compact rows r0 + rg + i * nrg
+      int64_t r = r0 + rg;
+      if (r < lo) r += (lo - r + nrg - 1) / nrg * nrg;
+      for (; r < hi; r += nrg) {
+        float4 v[NV];
+        load(r + shift, c, v);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { acc[i].x += v[i].x; acc[i].y += v[i].y; acc[i].z += v[i].z; acc[i].w += v[i].w; }
+      }
     }
 #pragma unroll
     for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(red + ((size_t)i * nrg + rg) * d)[c] = acc[i];
@@ -90,18 +144,21 @@ __device__ __forceinline__ bool finalize_sums(const float* __restrict__ partials
 
 // ------------------------------------------------------------------------------------------------ forward stats
 __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const float* __restrict__ out, int64_t ldo,
-                                                                      int64_t m, int d, float* __restrict__ partials) {
-  column_partials<2>(m, d, partials, [&](int64_t r, int c, float4* v) {
+                                                                      const RowMap rm, int d,
+                                                                      float* __restrict__ partials) {
+  const float* shift_row = out + (size_t)rm.padded(0) * ldo;
+  column_partials<2>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 x = ld_stream4(out + (size_t)r * ldo + 4 * c);
-    const float4 k = ldg4(out + 4 * c);  // shift = first row (exactly representable, cancels in the variance)
+    const float4 k = ldg4(shift_row + 4 * c);  // shift = first valid row (exact, cancels in the variance)
     const float4 dlt = make_float4(x.x - k.x, x.y - k.y, x.z - k.z, x.w - k.w);
     v[0] = dlt;
     v[1] = make_float4(dlt.x * dlt.x, dlt.y * dlt.y, dlt.z * dlt.z, dlt.w * dlt.w);
   });
 }
 
-__global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int n_part, const float* __restrict__ out,
-                                         int64_t m, int d, const float* __restrict__ gamma,
+__global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int n_part,
+                                         const float* __restrict__ shift_row, int64_t m, int d,
+                                         const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
                                          float* __restrict__ save_mean_rstd, float* __restrict__ coef) {
@@ -110,7 +167,7 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int
   const int c = blockIdx.x * 32 + threadIdx.x;
   const double s1 = s[0], s2 = s[1];
   const double n = (double)m;
-  const double mean = (double)out[c] + s1 / n;
+  const double mean = (double)shift_row[c] + s1 / n;
   double var = (s2 - s1 * s1 / n) / n;
   if (var < 0.0) var = 0.0;
   const float meanf = (float)mean, varf = (float)var;
@@ -141,12 +198,16 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ gamma, const fl
 template <bool RELU, bool RES>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ out, int64_t ldo,
                                                       const float* __restrict__ x_res, const float* __restrict__ coef,
-                                                      float* __restrict__ y, int64_t m, int d) {
+                                                      float* __restrict__ y, int64_t m, int d, const RowMap rm) {
   const int nchunk = d >> 2;
   const int64_t total = m * nchunk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nchunk;
     const int c = (int)(i - r * nchunk);
+    if (rm.n > 1 && !rm.valid(r)) {   // padding row of the structured layout stays zero
+      st_stream4(y + (size_t)r * d + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
     const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
     float4 z = make_float4((o.x - mu.x) * sc.x + be.x, (o.y - mu.y) * sc.y + be.y, (o.z - mu.z) * sc.z + be.z,
@@ -165,9 +226,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
 __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const float* __restrict__ gy,
                                                                     const float* __restrict__ out, int64_t ldo,
                                                                     const float* __restrict__ coef,
-                                                                    const float* __restrict__ mean_rstd, int64_t m,
-                                                                    int d, float* __restrict__ partials) {
-  column_partials<2>(m, d, partials, [&](int64_t r, int c, float4* v) {
+                                                                    const float* __restrict__ mean_rstd,
+                                                                    const RowMap rm, int d,
+                                                                    float* __restrict__ partials) {
+  column_partials<2>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
     const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
@@ -211,9 +273,10 @@ template <bool BF16>
 __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(
     const float* __restrict__ gy, const float* __restrict__ out, int64_t ldo, const float* __restrict__ coef,
     const float* __restrict__ mean_rstd, const float* __restrict__ g_gamma, const float* __restrict__ g_beta,
-    int64_t m, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg, float* __restrict__ partials) {
-  const float inv_m = 1.f / (float)m;
-  column_partials<1>(m, d, partials, [&](int64_t r, int c, float4* v) {
+    const RowMap rm, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg,
+    float* __restrict__ partials) {
+  const float inv_m = 1.f / (float)rm.total;
+  column_partials<1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
     const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
@@ -238,7 +301,10 @@ template <bool BF16>
 __global__ void __launch_bounds__(kColThreads) grad_prep_kernel(const float* __restrict__ g, int64_t ldg_in, int64_t m,
                                                                int d, void* __restrict__ g_hi, void* __restrict__ g_lo,
                                                                int64_t ldg, float* __restrict__ partials) {
-  column_partials<1>(m, d, partials, [&](int64_t r, int c, float4* v) {
+  RowMap rm;
+  rm.n = 1; rm.total = m; rm.cum[0] = 0; rm.cum[1] = rm.cum[2] = rm.cum[3] = rm.cum[4] = m;
+  rm.start[0] = rm.start[1] = rm.start[2] = rm.start[3] = 0;
+  column_partials<1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 x = ld_stream4(g + (size_t)r * ldg_in + 4 * c);
     store_g<BF16>(g_hi, g_lo, (size_t)r * ldg + 4 * c, x);
     v[0] = x;
@@ -260,21 +326,29 @@ extern "C" size_t pb_bn_workspace_bytes(int64_t m, int32_t d) {
   return align_up((size_t)col_ctas(m) * 2 * d * sizeof(float), 256);
 }
 
-extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const float* gamma, const float* beta,
-                           float eps, float momentum, float* running_mean, float* running_var, float* save_mean_rstd,
-                           float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups,
+                           const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                           float* running_var, float* save_mean_rstd, float* bn_coef, void* workspace,
+                           size_t workspace_bytes, pb_stream_t stream) {
   int rc = check_md(m, d, "pb_bn_stats");
   if (rc) return rc;
   PB_REQUIRE(out && gamma && beta && save_mean_rstd && bn_coef && workspace, "pb_bn_stats: null pointer");
   PB_REQUIRE(ldo >= d && ldo % 4 == 0, "pb_bn_stats: bad ldo");
   PB_REQUIRE(workspace_bytes >= pb_bn_workspace_bytes(m, d), "pb_bn_stats: workspace too small");
   cudaStream_t st = as_stream(stream);
-  const int ctas = col_ctas(m);
+  const RowMap rm = make_rowmap(groups, m);
+  const int64_t mv = valid_rows(rm);
+  PB_REQUIRE(mv > 0 && mv <= m, "pb_bn_stats: bad row groups");
+  const int ctas = col_ctas(mv);
   float* partials = reinterpret_cast<float*>(workspace);
-  bn_stats_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, m, d, partials);
+  bn_stats_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, rm, d, partials);
   PB_LAUNCH_CHECK();
-  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, out, m, d, gamma, beta, eps, momentum,
-                                                           running_mean, running_var, save_mean_rstd, bn_coef);
+  const float* shift_row = out + (size_t)(rm.n > 0 ? rm.start[0] + 0 : 0) * ldo;   // == padded(0) when group 0 is non-empty
+  for (int g = 0; g < rm.n; ++g)
+    if (rm.cum[g + 1] > rm.cum[g]) { shift_row = out + (size_t)rm.start[g] * ldo; break; }
+  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, shift_row, mv, d, gamma, beta, eps,
+                                                                           momentum, running_mean, running_var,
+                                                                           save_mean_rstd, bn_coef);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
@@ -289,7 +363,8 @@ extern "C" int pb_bn_prepare_eval(const float* gamma, const float* beta, const f
 }
 
 extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef, float* y,
-                                  int64_t m, int32_t d, int32_t apply_relu, pb_stream_t stream) {
+                                  int64_t m, int32_t d, const pb_groups_t* groups, int32_t apply_relu,
+                                  pb_stream_t stream) {
   int rc = check_md(m, d, "pb_bn_relu_res_fwd");
   if (rc) return rc;
   PB_REQUIRE(out && bn_coef && y, "pb_bn_relu_res_fwd: null pointer");
@@ -297,12 +372,13 @@ extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_
   const int64_t total = m * (d / 4);
   const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
   cudaStream_t st = as_stream(stream);
+  const RowMap rm = make_rowmap(groups, m);
   if (apply_relu) {
-    if (x_res) bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
-    else bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+    if (x_res) bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
+    else bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
   } else {
-    if (x_res) bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
-    else bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d);
+    if (x_res) bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
+    else bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
   }
   PB_LAUNCH_CHECK();
   return PB_OK;
@@ -310,8 +386,9 @@ extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_
 
 extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
                                   const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
-                                  int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma, float* g_beta,
-                                  float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+                                  const pb_groups_t* groups, int32_t dtype, void* g_hi, void* g_lo, int64_t ldg,
+                                  float* g_gamma, float* g_beta, float* g_bias, void* workspace,
+                                  size_t workspace_bytes, pb_stream_t stream) {
   int rc = check_md(m, d, "pb_bn_relu_res_bwd");
   if (rc) return rc;
   (void)gamma;
@@ -321,18 +398,21 @@ extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo
   PB_REQUIRE(ldo >= d && ldo % 4 == 0 && ldg >= d && ldg % 8 == 0, "pb_bn_relu_res_bwd: bad leading dimension");
   PB_REQUIRE(workspace_bytes >= pb_bn_workspace_bytes(m, d), "pb_bn_relu_res_bwd: workspace too small");
   cudaStream_t st = as_stream(stream);
-  const int ctas = col_ctas(m);
+  const RowMap rm = make_rowmap(groups, m);
+  const int64_t mv = valid_rows(rm);
+  PB_REQUIRE(mv > 0 && mv <= m, "pb_bn_relu_res_bwd: bad row groups");
+  const int ctas = col_ctas(mv);
   float* partials = reinterpret_cast<float*>(workspace);
-  bn_bwd_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, m, d, partials);
+  bn_bwd_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, rm, d, partials);
   PB_LAUNCH_CHECK();
   col_finalize_kernel<2><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_beta, g_gamma);
   PB_LAUNCH_CHECK();
   if (dtype == PB_BF16)
     bn_bwd_apply_kernel<true><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
-                                                                        g_beta, m, d, g_hi, g_lo, ldg, partials);
+                                                                        g_beta, rm, d, g_hi, g_lo, ldg, partials);
   else
     bn_bwd_apply_kernel<false><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
-                                                                         g_beta, m, d, g_hi, g_lo, ldg, partials);
+                                                                         g_beta, rm, d, g_hi, g_lo, ldg, partials);
   PB_LAUNCH_CHECK();
   if (g_bias) {
     col_finalize_kernel<1><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_bias, nullptr);

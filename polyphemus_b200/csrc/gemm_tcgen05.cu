@@ -130,13 +130,16 @@ static inline uint32_t make_idesc(bool bf16, int m, int n, int a_mn_major, int b
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+constexpr int kMaxSplits = 64;
+
 struct GemmParams {
   CUtensorMap tm_a[2];   // hi, lo
   CUtensorMap tm_b[2];
   int64_t m, n;          // output extent
   int a_mn_major, b_mn_major;
   int num_m_tiles, num_n_tiles, num_splits;
-  int k_blocks, k_blocks_per_split;
+  int k_blocks;
+  int split_kb[kMaxSplits + 1];   // split s contracts over k-blocks [split_kb[s], split_kb[s+1])
   uint32_t idesc;
   // epilogue
   void* out;             // fp32 or bf16
@@ -144,6 +147,12 @@ struct GemmParams {
   int64_t split_stride;  // elements between split-K partial outputs
   const float* bias;
   int out_bf16;
+  // structured (grouped) weight selection: rows of group g use Wcat block g for the first remap_d contraction /
+  // output columns and the shared blocks (offset +3*remap_d) for the rest
+  int remap_mode;        // 0 none, 1 remap B's k coordinate (forward), 2 remap B's row coordinate (input gradient)
+  int remap_d;
+  int n_groups;
+  long long grp_start[4];
 };
 
 template <bool BF16>
@@ -210,13 +219,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int split = t / tiles_mn, mn = t - split * tiles_mn;
         const int m0 = (mn / p.num_n_tiles) * C::BM, n0 = (mn % p.num_n_tiles) * C::BN;
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        const int kb0 = p.split_kb[split];
+        const int kb1 = p.split_kb[split + 1];
+        int grp = 0;
+        if (p.remap_mode) {   // last group whose first padded row is <= m0 (empty groups share their successor's start)
+          for (int g = p.n_groups - 1; g >= 0; --g)
+            if (p.grp_start[g] <= m0) { grp = g; break; }
+        }
+        const int n0_b = p.remap_mode == 2 ? (n0 < p.remap_d ? grp * p.remap_d + n0 : n0 + 3 * p.remap_d) : n0;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty + stage, phase ^ 1);
           uint8_t* st = smem + stage * C::kStageBytes;
           mbar_expect_tx(full + stage, C::kStageBytes);
           const int k0 = kb * C::BK;
+          const int k0_b = p.remap_mode == 1 ? (k0 < p.remap_d ? grp * p.remap_d + k0 : k0 + 3 * p.remap_d) : k0;
 #pragma unroll
           for (int s = 0; s < C::kSplit; ++s) {
             uint8_t* sa = st + s * C::kABytes;
@@ -231,9 +247,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
             if (p.b_mn_major) {
 #pragma unroll
               for (int i = 0; i < C::BN / C::kChunk; ++i)
-                tma_load_2d(&p.tm_b[s], full + stage, sb + i * (C::BK * 128), n0 + i * C::kChunk, k0);
+                tma_load_2d(&p.tm_b[s], full + stage, sb + i * (C::BK * 128), n0_b + i * C::kChunk, k0_b);
             } else {
-              tma_load_2d(&p.tm_b[s], full + stage, sb, k0, n0);
+              tma_load_2d(&p.tm_b[s], full + stage, sb, k0_b, n0_b);
             }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -250,8 +266,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0, buf_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int split = t / tiles_mn;
-        const int kb0 = split * p.k_blocks_per_split;
-        const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+        const int kb0 = p.split_kb[split];
+        const int kb1 = p.split_kb[split + 1];
         uint32_t d_tmem = 0, accum = 0;
         int in_chunk = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -344,8 +360,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
       const int split = t / tiles_mn, mn = t - split * tiles_mn;
       const int64_t m0 = (int64_t)(mn / p.num_n_tiles) * C::BM;
       const int n0 = (mn % p.num_n_tiles) * C::BN;
-      const int kb0 = split * p.k_blocks_per_split;
-      const int kb1 = min(kb0 + p.k_blocks_per_split, p.k_blocks);
+      const int kb0 = p.split_kb[split];
+      const int kb1 = p.split_kb[split + 1];
       const int64_t row0 = m0 + quad * 32;      // first row of this warp's TMEM lane quadrant
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
       if constexpr (BF16) {
@@ -412,6 +428,42 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, int n_split
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
     reinterpret_cast<float4*>(out)[i] = s;
+  }
+}
+
+// Structured weight gradient: partials [S][4d][d] from a split-K whose splits never straddle a row group.
+//   rows [0, d)   (track block)  : summed per group g into out rows [g*d, (g+1)*d)
+//   rows [d, 4d)  (onset, next, root blocks): summed over all splits into out rows [4d, 7d)
+struct SplitGroups { int n_splits; int group[kMaxSplits]; };
+__global__ void grouped_splitk_reduce_kernel(const float* __restrict__ part, const SplitGroups sg, int d,
+                                             float* __restrict__ out) {
+  const int n4 = d >> 2;
+  const int64_t total = (int64_t)4 * d * n4;
+  const size_t per_split = (size_t)4 * d * d;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n4), c4 = (int)(i - (int64_t)row * n4);
+    const float* src = part + (size_t)row * d + 4 * c4;
+    if (row >= d) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < sg.n_splits; ++s) {
+        const float4 v = ldg4(src + s * per_split);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      reinterpret_cast<float4*>(out + (size_t)(row + 3 * d) * d)[c4] = acc;
+    } else {
+      float4 acc[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < sg.n_splits; ++s) {
+        const float4 v = ldg4(src + s * per_split);
+        const int g = sg.group[s];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q == g) { acc[q].x += v.x; acc[q].y += v.y; acc[q].z += v.z; acc[q].w += v.w; }
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) reinterpret_cast<float4*>(out + (size_t)(g * d + row) * d)[c4] = acc[g];
+    }
   }
 }
 
@@ -519,7 +571,9 @@ struct Operand {
 
 template <bool BF16>
 static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n, int64_t k, void* out, int64_t ldd,
-                       bool out_bf16, const float* bias, int num_splits, int64_t split_stride, cudaStream_t st) {
+                       bool out_bf16, const float* bias, int num_splits, int64_t split_stride, cudaStream_t st,
+                       const pb_groups_t* groups = nullptr, int remap_mode = 0, int remap_d = 0,
+                       const int* split_table = nullptr) {
   using C = Cfg<BF16>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -537,15 +591,27 @@ static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n,
   p.num_m_tiles = (int)((m + C::BM - 1) / C::BM);
   p.num_n_tiles = (int)((n + C::BN - 1) / C::BN);
   p.k_blocks = (int)((k + C::BK - 1) / C::BK);
-  num_splits = std::max(1, std::min(num_splits, p.k_blocks));
-  p.k_blocks_per_split = (p.k_blocks + num_splits - 1) / num_splits;
-  p.num_splits = (p.k_blocks + p.k_blocks_per_split - 1) / p.k_blocks_per_split;
+  if (split_table) {   // caller-defined split boundaries (k-blocks), e.g. aligned to row groups
+    p.num_splits = num_splits;
+    for (int i = 0; i <= num_splits; ++i) p.split_kb[i] = split_table[i];
+  } else {
+    num_splits = std::max(1, std::min(std::min(num_splits, p.k_blocks), kMaxSplits));
+    const int per = (p.k_blocks + num_splits - 1) / num_splits;
+    p.num_splits = (p.k_blocks + per - 1) / per;
+    for (int i = 0; i <= p.num_splits; ++i) p.split_kb[i] = std::min(i * per, p.k_blocks);
+  }
   p.idesc = make_idesc(BF16, C::BM, C::BN, a.mn_major, b.mn_major);
   p.out = out;
   p.ldd = ldd;
   p.split_stride = split_stride;
   p.bias = bias;
   p.out_bf16 = out_bf16;
+  if (groups && remap_mode) {
+    p.remap_mode = remap_mode;
+    p.remap_d = remap_d;
+    p.n_groups = groups->n_groups;
+    for (int g = 0; g < groups->n_groups && g < 4; ++g) p.grp_start[g] = groups->start[g];
+  }
   const int64_t total = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_splits;
   const int grid = (int)std::min<int64_t>(total, sm_count());
   static bool attr_set = false;
@@ -566,6 +632,18 @@ static int check_gemm_dims(int64_t m, int d, int k, int dtype, const char* who) 
   return PB_OK;
 }
 
+// structured layout: 4 groups, starts on tile boundaries, d a multiple of the widest tile so that no tile straddles
+// two weight blocks, A width 4d
+static int check_groups(const pb_groups_t* g, int64_t m, int d, int k, const char* who) {
+  if (!g) return PB_OK;
+  PB_REQUIRE(g->n_groups == 4, "%s: structured mode expects 4 row groups", who);
+  PB_REQUIRE(d % 256 == 0, "%s: structured mode needs d %% 256 == 0 (got %d)", who, d);
+  PB_REQUIRE(k == 4 * d, "%s: structured mode expects k == 4*d", who);
+  for (int i = 0; i < 4; ++i)
+    PB_REQUIRE(g->start[i] % 128 == 0 && g->start[i] >= 0 && g->start[i] + g->count[i] <= m, "%s: bad row group %d", who, i);
+  return PB_OK;
+}
+
 static int bwd_weight_splits(int64_t m, int d, int k, bool bf16) {
   const int bm = 128, bn = bf16 ? 256 : 128, bk = bf16 ? 64 : 32;
   const int64_t tiles = (int64_t)((k + bm - 1) / bm) * ((d + bn - 1) / bn);
@@ -581,17 +659,20 @@ using namespace pb;
 
 extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
                                 const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
-                                int32_t k, int32_t dtype, pb_stream_t stream) {
+                                int32_t k, const pb_groups_t* groups, int32_t dtype, pb_stream_t stream) {
   int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_fwd");
   if (rc) return rc;
   PB_REQUIRE(a_hi && wcat_t_hi && out, "pb_rgcn_gemm_fwd: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (a_lo && wcat_t_lo), "pb_rgcn_gemm_fwd: PB_F32 needs lo operands");
   PB_REQUIRE(lda >= k && lda % 8 == 0 && ldo >= d && ldo % 4 == 0, "pb_rgcn_gemm_fwd: bad leading dimension");
+  int rc2 = check_groups(groups, m, d, k, "pb_rgcn_gemm_fwd");
+  if (rc2) return rc2;
+  const int kw = groups ? (groups->n_groups + 3) * d : k;     // K extent of the weight operand
   Operand a{a_hi, a_lo, m, k, lda, false};
-  Operand b{wcat_t_hi, wcat_t_lo, d, k, k, false};
+  Operand b{wcat_t_hi, wcat_t_lo, d, kw, kw, false};
   cudaStream_t st = as_stream(stream);
-  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st)
-                        : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d)
+                        : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d);
   return rc < 0 ? rc : PB_OK;
 }
 
@@ -615,17 +696,20 @@ extern "C" int pb_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const
 
 extern "C" int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
                                      const void* wcat_lo, void* d_a, int64_t ldda, int64_t m, int32_t d, int32_t k,
-                                     int32_t dtype, pb_stream_t stream) {
+                                     const pb_groups_t* groups, int32_t dtype, pb_stream_t stream) {
   int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_bwd_data");
   if (rc) return rc;
   PB_REQUIRE(g_hi && wcat_hi && d_a, "pb_rgcn_gemm_bwd_data: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (g_lo && wcat_lo), "pb_rgcn_gemm_bwd_data: PB_F32 needs lo operands");
   PB_REQUIRE(ldg >= d && ldg % 8 == 0 && ldda >= k && ldda % 8 == 0, "pb_rgcn_gemm_bwd_data: bad leading dimension");
+  int rc2 = check_groups(groups, m, d, k, "pb_rgcn_gemm_bwd_data");
+  if (rc2) return rc2;
+  const int kw = groups ? (groups->n_groups + 3) * d : k;     // rows of the weight operand
   Operand a{g_hi, g_lo, m, d, ldg, false};          // [M, d], contraction over d
-  Operand b{wcat_hi, wcat_lo, k, d, d, false};      // Wcat [K, d]: rows = output columns, K-major in d
+  Operand b{wcat_hi, wcat_lo, kw, d, d, false};     // Wcat [K, d]: rows = output columns, K-major in d
   cudaStream_t st = as_stream(stream);
-  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, k, d, d_a, ldda, true, nullptr, 1, 0, st)
-                        : launch_gemm<false>(a, b, m, k, d, d_a, ldda, false, nullptr, 1, 0, st);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, k, d, d_a, ldda, true, nullptr, 1, 0, st, groups, 2, d)
+                        : launch_gemm<false>(a, b, m, k, d, d_a, ldda, false, nullptr, 1, 0, st, groups, 2, d);
   return rc < 0 ? rc : PB_OK;
 }
 
@@ -633,7 +717,7 @@ static inline int64_t pad4(int64_t v) { return (v + 3) / 4 * 4; }
 
 extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k) {
   if (m <= 0 || d <= 0 || k <= 0) return 0;
-  const int s = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false));
+  const int s = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false)) + 4;  // +4: per-group minimum
   const size_t partials = align_up((size_t)s * k * d * sizeof(float), 256);
   const size_t transposed = 2 * (align_up((size_t)k * pad4(m) * sizeof(float), 256) +
                                  align_up((size_t)d * pad4(m) * sizeof(float), 256));   // PB_F32 only
@@ -642,26 +726,56 @@ extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, 
 
 extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
                                        const void* g_lo, int64_t ldg, float* d_wcat, int64_t m, int32_t d, int32_t k,
-                                       int32_t dtype, void* workspace, size_t workspace_bytes, pb_stream_t stream) {
+                                       const pb_groups_t* groups, int32_t dtype, void* workspace,
+                                       size_t workspace_bytes, pb_stream_t stream) {
   int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_bwd_weight");
   if (rc) return rc;
+  if ((rc = check_groups(groups, m, d, k, "pb_rgcn_gemm_bwd_weight"))) return rc;
   PB_REQUIRE(a_hi && g_hi && d_wcat && workspace, "pb_rgcn_gemm_bwd_weight: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (a_lo && g_lo), "pb_rgcn_gemm_bwd_weight: PB_F32 needs lo operands");
   PB_REQUIRE(lda >= k && lda % 8 == 0 && ldg >= d && ldg % 8 == 0, "pb_rgcn_gemm_bwd_weight: bad leading dimension");
   PB_REQUIRE(workspace_bytes >= pb_rgcn_gemm_bwd_weight_workspace_bytes(m, d, k), "pb_rgcn_gemm_bwd_weight: workspace too small");
   const bool bf16 = dtype == PB_BF16;
-  const int splits = bwd_weight_splits(m, d, k, bf16);
+  int splits = bwd_weight_splits(m, d, k, bf16);
   cudaStream_t st = as_stream(stream);
   float* part = reinterpret_cast<float*>(workspace);
   const int64_t n_elems = (int64_t)k * d;
+  // structured layout: split boundaries follow the row groups so that the track block can be reduced per group
+  int table[kMaxSplits + 1];
+  SplitGroups sg;
+  memset(&sg, 0, sizeof(sg));
+  const int* split_table = nullptr;
+  if (groups) {
+    const int bk = bf16 ? 64 : 32;
+    const int64_t n_valid = groups->count[0] + groups->count[1] + groups->count[2] + groups->count[3];
+    const int budget = std::max(1, std::min(splits, kMaxSplits - 4));
+    int ns = 0;
+    for (int g = 0; g < 4; ++g) {
+      if (groups->count[g] <= 0) continue;
+      const int kb_begin = (int)(groups->start[g] / bk);   // group starts are multiples of 128
+      const int kb_end = (int)((groups->start[g] + groups->count[g] + bk - 1) / bk);
+      int cnt = (int)std::max<int64_t>(1, (int64_t)budget * groups->count[g] / std::max<int64_t>(1, n_valid));
+      cnt = std::min(cnt, kb_end - kb_begin);
+      for (int i = 0; i < cnt; ++i) {
+        table[ns] = kb_begin + (int)((int64_t)(kb_end - kb_begin) * i / cnt);
+        sg.group[ns++] = g;
+      }
+    }
+    PB_REQUIRE(ns > 0, "pb_rgcn_gemm_bwd_weight: empty row groups");
+    // split s covers [table[s], table[s+1]): the last split of a group runs on over the group's zero padding
+    table[ns] = (int)((m + bk - 1) / bk);
+    sg.n_splits = ns;
+    splits = ns;
+    split_table = table;
+  }
   if (bf16) {
     Operand a{a_hi, a_lo, m, k, lda, true};   // stored [nodes, K]: output rows (K) contiguous -> MN-major
     Operand b{g_hi, g_lo, m, d, ldg, true};   // stored [nodes, d]
-    rc = launch_gemm<true>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+    rc = launch_gemm<true>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st, nullptr, 0, 0, split_table);
   } else {
     // K-major transposed copies: At [K, m], gt [d, m]
     const int64_t mp = pad4(m);
-    const int s_max = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false));
+    const int s_max = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false)) + 4;
     char* wsp = reinterpret_cast<char*>(workspace) + align_up((size_t)s_max * k * d * sizeof(float), 256);
     float* at_hi = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)k * mp * sizeof(float), 256);
     float* at_lo = reinterpret_cast<float*>(wsp); wsp += align_up((size_t)k * mp * sizeof(float), 256);
@@ -673,12 +787,15 @@ extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64
     if ((rc = transpose_f32(reinterpret_cast<const float*>(g_lo), m, d, ldg, gt_lo, mp, st))) return rc;
     Operand a{at_hi, at_lo, k, m, mp, false};
     Operand b{gt_hi, gt_lo, d, m, mp, false};
-    rc = launch_gemm<false>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st);
+    rc = launch_gemm<false>(a, b, k, d, m, part, d, false, nullptr, splits, n_elems, st, nullptr, 0, 0, split_table);
   }
   if (rc < 0) return rc;
   const int used = rc;
   const unsigned grid = (unsigned)std::min<int64_t>((n_elems / 4 + 255) / 256, (int64_t)sm_count() * 8);
-  splitk_reduce_kernel<<<grid, 256, 0, st>>>(part, used, n_elems, d_wcat);
+  if (groups)
+    grouped_splitk_reduce_kernel<<<grid, 256, 0, st>>>(part, sg, d, d_wcat);   // d_wcat is [7d, d] here
+  else
+    splitk_reduce_kernel<<<grid, 256, 0, st>>>(part, used, n_elems, d_wcat);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

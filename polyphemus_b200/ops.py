@@ -36,6 +36,19 @@ _seed_counter = itertools.count()
 launch_counter = _ffi.launch_counter
 
 
+_structured = os.environ.get("PB200_STRUCTURED", "1") != "0"
+
+
+def set_structured(enabled: bool) -> None:
+    """Use the track-relation-sorted 4d-wide operand layout inside GCN stacks when the graph allows it."""
+    global _structured
+    _structured = bool(enabled)
+
+
+def structured_enabled() -> bool:
+    return _structured
+
+
 def set_precision(name: str) -> None:
     """'fp32' (TF32x3 tensor-core mode, fp32-grade) or 'bf16' (bf16 operands, fp32 accumulate)."""
     global _default_precision
@@ -48,8 +61,8 @@ def get_precision() -> str:
     return _default_precision
 
 
-def _call(name: str, *args) -> None:
-    _ffi.call(name, *args)
+def _call(name: str, *args, tag=None) -> None:
+    _ffi.call(name, *args, tag=tag)
 
 
 def next_seed() -> int:
@@ -70,11 +83,12 @@ class LayerConfig:
     momentum: float = BN_MOMENTUM
 
 
-def _operand(n: int, k: int, dtype: int, dev):
+def _operand(n: int, k: int, dtype: int, dev, zero: bool = False):
     """GEMM operand buffers in the arithmetic mode's storage: bf16, or TF32 hi/lo fp32 pair."""
+    make = torch.zeros if zero else torch.empty
     if dtype == _ffi.PB_BF16:
-        return torch.empty((n, k), dtype=torch.bfloat16, device=dev), None
-    return torch.empty((n, k), dtype=torch.float32, device=dev), torch.empty((n, k), dtype=torch.float32, device=dev)
+        return make((n, k), dtype=torch.bfloat16, device=dev), None
+    return make((n, k), dtype=torch.float32, device=dev), make((n, k), dtype=torch.float32, device=dev)
 
 
 def _edge_table(nn_w: torch.Tensor, nn_b: torch.Tensor, d: int, st: int) -> torch.Tensor:
@@ -112,18 +126,20 @@ class RGCLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var,
-                plan: CsrPlan, cfg: LayerConfig):
+                plan: CsrPlan, cfg: LayerConfig, struct=None):
         _ffi.require_cuda(x, weight, root, nn_w, nn_b)
         if x.dtype != torch.float32:
             raise TypeError("node features must be float32 (the arithmetic mode is chosen by `precision`)")
         x = x.contiguous()
         n, d = x.shape
-        r = plan.n_relations
-        if weight.shape != (r, d, d) or root.shape != (d, d):
+        r = plan.n_relations                     # operand blocks per node: R, or 3 slots in the structured layout
+        n_w = weight.shape[0]
+        if weight.shape != (n_w, d, d) or root.shape != (d, d) or (struct is None and n_w != r):
             raise ValueError("the CUDA path supports in_channels == out_channels == d, weight [R,d,d], root [d,d]")
         if n != plan.n_nodes:
             raise ValueError(f"x has {n} rows but the graph has {plan.n_nodes} nodes")
         k = (r + 1) * d
+        groups = None if struct is None else struct.groups_ref()
         dev = x.device
         weight, root = weight.contiguous(), root.contiguous()
         nn_w, nn_b = nn_w.contiguous(), nn_b.contiguous()
@@ -137,11 +153,12 @@ class RGCLayerFn(torch.autograd.Function):
             _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
                   cfg.dtype, _ffi.ptr(keep_bits), p, st)
             ctx.keep_bits = keep_bits
-            _, _, wt_hi, wt_lo = _weights(weight, root, r, d, cfg.dtype, st)
+            _, _, wt_hi, wt_lo = _weights(weight, root, n_w, d, cfg.dtype, st)
             out = torch.empty((n, d), dtype=torch.float32, device=dev)
             _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
-                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, cfg.dtype, st)
+                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, st)
             ctx.operand = (a_hi, a_lo) if cfg.save_operand else None
+            ctx.struct = struct
             if not cfg.batch_norm:
                 ctx.save_for_backward(x, weight, root, nn_w, nn_b)
                 ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
@@ -151,14 +168,14 @@ class RGCLayerFn(torch.autograd.Function):
             if cfg.training:
                 ws_bytes = _ffi.lib().pb_bn_workspace_bytes(n, d)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                _call("pb_bn_stats", out.data_ptr(), d, n, d, gamma.data_ptr(), beta.data_ptr(), cfg.eps, cfg.momentum,
-                      _ffi.ptr(running_mean), _ffi.ptr(running_var), save.data_ptr(), coef.data_ptr(), ws.data_ptr(),
-                      ws_bytes, st)
+                _call("pb_bn_stats", out.data_ptr(), d, n, d, groups, gamma.data_ptr(), beta.data_ptr(), cfg.eps,
+                      cfg.momentum, _ffi.ptr(running_mean), _ffi.ptr(running_var), save.data_ptr(), coef.data_ptr(),
+                      ws.data_ptr(), ws_bytes, st)
             else:
                 _call("pb_bn_prepare_eval", gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
                       running_var.data_ptr(), cfg.eps, d, coef.data_ptr(), st)
             y = torch.empty((n, d), dtype=torch.float32, device=dev)
-            _call("pb_bn_relu_res_fwd", out.data_ptr(), d, x.data_ptr(), coef.data_ptr(), y.data_ptr(), n, d, 1, st)
+            _call("pb_bn_relu_res_fwd", out.data_ptr(), d, x.data_ptr(), coef.data_ptr(), y.data_ptr(), n, d, groups, 1, st)
         ctx.save_for_backward(x, weight, root, nn_w, nn_b, gamma, out, coef, save)
         ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
         return y
@@ -176,12 +193,15 @@ class RGCLayerFn(torch.autograd.Function):
             x, weight, root, nn_w, nn_b = ctx.saved_tensors
         n, d = x.shape
         r = plan.n_relations
+        n_w = weight.shape[0]
         k = (r + 1) * d
         dev = x.device
         lib = _ffi.lib()
+        struct = ctx.struct
+        groups = None if struct is None else struct.groups_ref()
         with torch.cuda.device(dev):
             st = _ffi.stream()
-            g_hi, g_lo = _operand(n, d, cfg.dtype, dev)
+            g_hi, g_lo = _operand(n, d, cfg.dtype, dev, zero=struct is not None)   # padding rows must stay zero
             g_bias = torch.empty(d, dtype=torch.float32, device=dev)
             ws_bytes = lib.pb_bn_workspace_bytes(n, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -190,7 +210,7 @@ class RGCLayerFn(torch.autograd.Function):
                 g_gamma = torch.empty(d, dtype=torch.float32, device=dev)
                 g_beta = torch.empty(d, dtype=torch.float32, device=dev)
                 _call("pb_bn_relu_res_bwd", gy.data_ptr(), out.data_ptr(), d, gamma.data_ptr(), save.data_ptr(),
-                      coef.data_ptr(), n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d, g_gamma.data_ptr(),
+                      coef.data_ptr(), n, d, groups, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d, g_gamma.data_ptr(),
                       g_beta.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
             else:
                 _call("pb_grad_prep", gy.data_ptr(), d, n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
@@ -204,16 +224,19 @@ class RGCLayerFn(torch.autograd.Function):
                 a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
                 _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
                       cfg.dtype, _ffi.ptr(ctx.keep_bits), p, st)
-            w_hi, w_lo, _, _ = _weights(weight, root, r, d, cfg.dtype, st)
-            d_wcat = torch.empty((k, d), dtype=torch.float32, device=dev)
+            w_hi, w_lo, _, _ = _weights(weight, root, n_w, d, cfg.dtype, st)
+            kw = (n_w + 1) * d
+            # structured layout: one split-K launch whose splits follow the row groups + a grouped reduce that sums
+            # the track block per group (weight[0..3]) and the onset / next / root blocks over all rows
+            d_wcat = torch.empty((kw, d), dtype=torch.float32, device=dev)
             wws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, d, k)
             wws = torch.empty(wws_bytes, dtype=torch.uint8, device=dev)
             _call("pb_rgcn_gemm_bwd_weight", a_hi.data_ptr(), _ffi.ptr(a_lo), k, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
-                  d_wcat.data_ptr(), n, d, k, cfg.dtype, wws.data_ptr(), wws_bytes, st)
+                  d_wcat.data_ptr(), n, d, k, groups, cfg.dtype, wws.data_ptr(), wws_bytes, st)
             del a_hi, a_lo, wws
             d_a = torch.empty((n, k), dtype=torch.bfloat16 if cfg.dtype == _ffi.PB_BF16 else torch.float32, device=dev)
             _call("pb_rgcn_gemm_bwd_data", g_hi.data_ptr(), _ffi.ptr(g_lo), d, w_hi.data_ptr(), _ffi.ptr(w_lo),
-                  d_a.data_ptr(), k, n, d, k, cfg.dtype, st)
+                  d_a.data_ptr(), k, n, d, k, groups, cfg.dtype, st)
             gx = torch.empty((n, d), dtype=torch.float32, device=dev)
             q_buf = torch.empty((max(plan.n_edges, 1), d), dtype=d_a.dtype, device=dev)
             partials = torch.empty((plan.n_dist_items, d), dtype=torch.float32, device=dev)
@@ -224,10 +247,10 @@ class RGCLayerFn(torch.autograd.Function):
             g_nn_b = torch.empty(d, dtype=torch.float32, device=dev)
             _call("pb_edge_table_bwd", partials.data_ptr(), plan.dist_item_ptr.data_ptr(), d, g_nn_w.data_ptr(),
                   g_nn_b.data_ptr(), st)
-        g_weight = d_wcat[: r * d].view(r, d, d)
-        g_root = d_wcat[r * d:]
+        g_weight = d_wcat[: n_w * d].view(n_w, d, d)
+        g_root = d_wcat[n_w * d:]
         return (gx, g_weight, g_root, g_bias if ctx.has_bias else None, g_nn_w, g_nn_b, g_gamma, g_beta,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 # Operands up to this size are kept for backward (LMD16, per-GPU batch 256, bf16: 0.94 GB per layer); larger ones
@@ -238,7 +261,7 @@ SAVE_OPERAND_MAX_BYTES = int(os.environ.get("PB200_SAVE_OPERAND_MB", "2048")) <<
 def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, beta=None, running_mean=None,
               running_var=None, batch_norm: bool, training: bool, p_drop: float, precision: Optional[str] = None,
               seed: Optional[int] = None, eps: float = BN_EPS, momentum: float = BN_MOMENTUM,
-              save_operand: Optional[bool] = None):
+              save_operand: Optional[bool] = None, struct=None):
     dtype = _PRECISIONS[precision or _default_precision]
     if save_operand is None:
         elem = 2 if dtype == _ffi.PB_BF16 else 8
@@ -248,7 +271,8 @@ def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, b
                       seed=next_seed() if seed is None else int(seed), training=bool(training),
                       batch_norm=bool(batch_norm), save_operand=bool(save_operand), eps=float(eps),
                       momentum=float(momentum))
-    return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg)
+    return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg,
+                            struct)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -281,7 +305,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
         bias_f = None if bias is None else bias.float().contiguous()
         with torch.cuda.device(dev):
             _call("pb_gemm_nt", x_hi.data_ptr(), _ffi.ptr(x_lo), k, w_hi.data_ptr(), _ffi.ptr(w_lo), k,
-                  _ffi.ptr(bias_f), out.data_ptr(), n, m, n, k, dtype, int(out_bf16), _ffi.stream())
+                  _ffi.ptr(bias_f), out.data_ptr(), n, m, n, k, dtype, int(out_bf16), _ffi.stream(), tag="linear")
         ctx.save_for_backward(x_hi, x_lo, weight)
         ctx.dtype, ctx.has_bias, ctx.x_dtype = dtype, bias is not None, x.dtype
         return out
@@ -303,7 +327,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
                 dx_bf16 = dtype == _ffi.PB_BF16 and ctx.x_dtype == torch.bfloat16
                 dx = torch.empty((m, k), dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev)
                 _call("pb_gemm_nt", g_hi.data_ptr(), _ffi.ptr(g_lo), n, wt_hi.data_ptr(), _ffi.ptr(wt_lo), n, None,
-                      dx.data_ptr(), k, m, k, n, dtype, int(dx_bf16), st)
+                      dx.data_ptr(), k, m, k, n, dtype, int(dx_bf16), st, tag="linear")
             dw = None
             if ctx.needs_input_grad[1]:
                 dw = torch.empty((n, k), dtype=torch.float32, device=dev)
@@ -311,7 +335,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 # dW[n, k] = g^T @ x: the split-K kernel contracts over the rows of its two [m, .] operands
                 _call("pb_rgcn_gemm_bwd_weight", g_hi.data_ptr(), _ffi.ptr(g_lo), n, x_hi.data_ptr(), _ffi.ptr(x_lo), k,
-                      dw.data_ptr(), m, k, n, dtype, ws.data_ptr(), ws_bytes, st)
+                      dw.data_ptr(), m, k, n, None, dtype, ws.data_ptr(), ws_bytes, st, tag="linear")
         db = g.sum(0, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None, None
 

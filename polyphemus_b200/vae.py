@@ -298,11 +298,32 @@ class ContentDecoder(nn.Module):
         h_dur = self.dropout_layer(h_dur).view(-1, t, half)
         # both pitch heads on every node, then select per node: no compaction, no host sync
         is_drum = s.is_drum.view(-1, 1, 1)
+        if h.is_cuda:
+            # un-embedding heads (131 / 99 outputs) on the tcgen05 GEMM: output width padded to a multiple of 64 with
+            # zero weight rows and a -inf bias, so the padded logits vanish from every softmax downstream
+            drums = _padded_head(self.drums_pitch_emb, h_pitch)
+            others = _padded_head(self.non_drums_pitch_emb, h_pitch)
+            pitch_pad = torch.where(is_drum, drums, others)
+            dur_pad = _padded_head(self.dur_emb, h_dur)
+            pitch, dur = pitch_pad[..., :N_PITCH_TOKENS], dur_pad[..., :N_DUR_TOKENS]
+            c_logits = torch.cat((pitch, dur), dim=-1)
+            c_logits._parts = (pitch_pad, dur_pad)   # lets the loss skip re-slicing (padding columns are -inf)
+            return c_logits
         pitch = torch.where(is_drum, self.drums_pitch_emb(h_pitch), self.non_drums_pitch_emb(h_pitch))
         dur = self.dur_emb(h_dur)
         c_logits = torch.cat((pitch, dur), dim=-1)
         c_logits._parts = (pitch, dur)          # lets the loss skip re-slicing the concatenation
         return c_logits
+
+
+def _padded_head(lin: nn.Linear, h: torch.Tensor) -> torch.Tensor:
+    """lin(h) for h [n, t, k] with the output width padded up to a multiple of 64: [n, t, n_pad] fp32, padding = -inf."""
+    n_out, k = lin.weight.shape
+    pad = (-n_out) % 64
+    w = F.pad(lin.weight, (0, 0, 0, pad))
+    b = F.pad(lin.bias, (0, pad), value=float("-inf"))
+    out = ops.tc_linear(h.reshape(-1, k), w, b)
+    return out.view(*h.shape[:-1], n_out + pad)
 
 
 class Decoder(nn.Module):

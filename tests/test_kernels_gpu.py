@@ -73,7 +73,7 @@ def test_gemm_fwd(cuda, dtype_name, m, d):
     w_hi, w_lo = operands(wt, dtype)
     out = torch.full((m, d), float("nan"), device=cuda)
     ffi.check(ffi.lib().pb_rgcn_gemm_fwd(ptr(a_hi), ptr(a_lo), k, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), d, m, d, k,
-                                         dtype, st()), "pb_rgcn_gemm_fwd")
+                                         None, dtype, st()), "pb_rgcn_gemm_fwd")
     torch.cuda.synchronize()
     ref = as_f64(a_hi, a_lo) @ as_f64(w_hi, w_lo).t() + bias.double()
     tol = dict(rtol=2e-3, atol=2e-3) if dtype_name == "bf16" else F32_TOL
@@ -99,7 +99,7 @@ def test_gemm_bwd_data(cuda, dtype_name, m, d):
     g_hi, g_lo = operands(g, dtype)
     w_hi, w_lo = operands(w, dtype)
     d_a = torch.empty((m, k), dtype=torch.bfloat16 if dtype == ffi.PB_BF16 else torch.float32, device=cuda)
-    ffi.check(ffi.lib().pb_rgcn_gemm_bwd_data(ptr(g_hi), ptr(g_lo), d, ptr(w_hi), ptr(w_lo), ptr(d_a), k, m, d, k, dtype,
+    ffi.check(ffi.lib().pb_rgcn_gemm_bwd_data(ptr(g_hi), ptr(g_lo), d, ptr(w_hi), ptr(w_lo), ptr(d_a), k, m, d, k, None, dtype,
                                               st()), "pb_rgcn_gemm_bwd_data")
     ref = as_f64(g_hi, g_lo) @ as_f64(w_hi, w_lo).t()
     tol = dict(rtol=1e-2, atol=1e-2) if dtype_name == "bf16" else F32_TOL   # bf16 output rounding
@@ -121,14 +121,14 @@ def test_gemm_bwd_weight(cuda, dtype_name, m, d):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
     d_w = torch.full((k, d), float("nan"), device=cuda)
     ffi.check(ffi.lib().pb_rgcn_gemm_bwd_weight(ptr(a_hi), ptr(a_lo), k, ptr(g_hi), ptr(g_lo), d, ptr(d_w), m, d, k,
-                                                dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
+                                                None, dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
     ref = as_f64(a_hi, a_lo).t() @ as_f64(g_hi, g_lo)
     tol = dict(rtol=2e-3, atol=2e-3) if dtype_name == "bf16" else F32_TOL
     torch.testing.assert_close(d_w.double(), ref, **tol)
     # determinism of the split-K reduction
     d_w2 = torch.empty_like(d_w)
     ffi.check(ffi.lib().pb_rgcn_gemm_bwd_weight(ptr(a_hi), ptr(a_lo), k, ptr(g_hi), ptr(g_lo), d, ptr(d_w2), m, d, k,
-                                                dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
+                                                None, dtype, ptr(ws), ws_bytes, st()), "pb_rgcn_gemm_bwd_weight")
     assert torch.equal(d_w, d_w2)
 
 
@@ -275,10 +275,10 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     ws_bytes = lib.pb_bn_workspace_bytes(m, d)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
     coef, save = torch.empty(3, d, device=cuda), torch.empty(2, d, device=cuda)
-    ffi.check(lib.pb_bn_stats(ptr(out_d), d, m, d, ptr(gamma_d), ptr(beta_d), 1e-5, 0.1, ptr(rm_d), ptr(rv_d), ptr(save),
-                              ptr(coef), ptr(ws), ws_bytes, st()), "bn_stats")
+    ffi.check(lib.pb_bn_stats(ptr(out_d), d, m, d, None, ptr(gamma_d), ptr(beta_d), 1e-5, 0.1, ptr(rm_d), ptr(rv_d),
+                              ptr(save), ptr(coef), ptr(ws), ws_bytes, st()), "bn_stats")
     y = torch.empty(m, d, device=cuda)
-    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef), ptr(y), m, d, 1, st()), "bn_fwd")
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef), ptr(y), m, d, None, 1, st()), "bn_fwd")
     torch.testing.assert_close(y.double().cpu(), y_ref, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(rm_d.double().cpu(), rm64, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(rv_d.double().cpu(), rv64, rtol=1e-4, atol=1e-5)
@@ -297,7 +297,7 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     g_out_ref = sc32.double() * (gz - g_beta_ref / m - xhat * g_gamma_ref / m)
     g_hi, g_lo = torch.empty(m, d, device=cuda), torch.empty(m, d, device=cuda)
     g_gamma, g_beta, g_bias = (torch.empty(d, device=cuda) for _ in range(3))
-    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, ffi.PB_F32,
+    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, None, ffi.PB_F32,
                                      ptr(g_hi), ptr(g_lo), d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
                                      st()), "bn_bwd")
     scale = float(g_out_ref.abs().max())
@@ -314,14 +314,14 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     if cols.any():
         torch.testing.assert_close(g_out_ref[:, cols], o64.grad[:, cols], rtol=1e-4, atol=1e-5 * max(1.0, scale))
     g_bf = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
-    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, ffi.PB_BF16,
+    ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, None, ffi.PB_BF16,
                                      ptr(g_bf), None, d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
                                      st()), "bn_bwd")
     torch.testing.assert_close(g_bf.double().cpu(), g_out_ref, rtol=1e-2, atol=1e-2 * max(1.0, scale))
     # eval mode coefficients
     coef_e = torch.empty(3, d, device=cuda)
     ffi.check(lib.pb_bn_prepare_eval(ptr(gamma_d), ptr(beta_d), ptr(rm_d), ptr(rv_d), 1e-5, d, ptr(coef_e), st()), "bn_eval")
-    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef_e), ptr(y), m, d, 1, st()), "bn_fwd")
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef_e), ptr(y), m, d, None, 1, st()), "bn_fwd")
     y_eval = x.double() + torch.relu(torch.nn.functional.batch_norm(out.double(), rm_d.double().cpu(), rv_d.double().cpu(),
                                                                     gamma.double(), beta.double(), False, 0.1, 1e-5))
     torch.testing.assert_close(y.double().cpu(), y_eval, rtol=1e-4, atol=2e-5)

@@ -339,3 +339,109 @@ def test_layer_is_bit_reproducible(cuda):
                      gcn.layers[0].nn.weight.grad.clone()))
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+def _structured_case(cuda, d=256, precision="fp32", p_gcl=0.0, seed=0):
+    """A GCN stack on a builder graph with every special case of the structured layout: an empty bar (fake node),
+    single-node bars on tracks 0 and 2 (group 0 through the fake self-edge), a full bar, empty groups elsewhere."""
+    import polyphemus_b200 as pb
+
+    s_np = go.synthetic_structure(5, 3, 0.3, seed=seed)
+    s_np[0, 1] = False                       # empty bar
+    s_np[1, 0] = False
+    s_np[1, 0, 2, 9] = True                  # one node, track 2
+    s_np[2, 2] = False
+    s_np[2, 2, 0, 0] = True                  # one node, track 0
+    s_np[3, 1] = True                        # full bar
+    arrays = go.batch_graph(s_np)
+    graph = pb.graphs_from_tensor(torch.from_numpy(s_np).to(cuda))
+    torch.manual_seed(seed)
+    gcn = pb.GCN(input_dim=d, hidden_dim=d, n_layers=2, num_relations=6, batch_norm=True, dropout=0, precision=precision)
+    for layer in gcn.layers:
+        layer.dropout = p_gcl
+    with torch.no_grad():
+        for prm in gcn.parameters():
+            if prm.dim() == 1:
+                prm.add_(0.1 * torch.randn_like(prm))
+    sd = {k: v.detach().clone() for k, v in gcn.state_dict().items()}
+    gen = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(arrays.num_nodes, d, generator=gen)
+    gy = torch.randn(arrays.num_nodes, d, generator=gen)
+    return gcn.to(cuda).train(), sd, graph, arrays, x, gy
+
+
+def _run_gcn(gcn, graph, x, gy, cuda):
+    for prm in gcn.parameters():
+        prm.grad = None
+    graph.x = x.to(cuda).requires_grad_(True)
+    y = gcn(graph)
+    y.backward(gy.to(cuda))
+    grads = {k: p.grad.detach().cpu().clone() for k, p in gcn.named_parameters()}
+    stats = {k: v.detach().cpu().clone() for k, v in gcn.state_dict().items() if "running" in k}
+    return y.detach().cpu(), graph.x.grad.cpu(), grads, stats
+
+
+def test_structured_layout_matches_generic_and_oracle(cuda):
+    """Track-relation-sorted 4d-wide operand == generic 7d-wide path == oracle, fwd + all gradients."""
+    from polyphemus_b200 import ops
+
+    gcn, sd, graph, arrays, x, gy = _structured_case(cuda)
+    st = graph.structured
+    assert st is not None and sum(st.counts) == arrays.num_nodes and st.n_padded % 128 == 0
+    # group of a node: its track, except the lone node of a one-node bar (fake self-edge of type 0)
+    grp = graph.node_group.cpu().numpy()
+    bar_id = (graph.bars + 3 * graph.batch).cpu().numpy()
+    lone = np.bincount(bar_id)[bar_id] == 1
+    np.testing.assert_array_equal(grp, np.where(lone, 0, arrays.node_features.argmax(1)))
+    try:
+        ops.set_structured(True)
+        y_s, gx_s, g_s, st_s = _run_gcn(gcn, graph, x, gy, cuda)
+        gcn.load_state_dict(sd)
+        ops.set_structured(False)
+        y_g, gx_g, g_g, st_g = _run_gcn(gcn, graph, x, gy, cuda)
+    finally:
+        ops.set_structured(True)
+    torch.testing.assert_close(y_s, y_g, **TOL)
+    torch.testing.assert_close(gx_s, gx_g, rtol=1e-4, atol=1e-5)
+    for k in g_g:
+        atol = 3e-4 if (k.endswith(".bias") and "norm_layers" not in k) else 1e-5 * max(1.0, float(g_g[k].abs().max()))
+        torch.testing.assert_close(g_s[k], g_g[k], rtol=1e-4, atol=atol, msg=k)
+    for k in st_g:
+        torch.testing.assert_close(st_s[k], st_g[k], rtol=1e-5, atol=1e-6, msg=k)
+    # oracle
+    osd = mo.leaf_state({"g." + k: v for k, v in sd.items()})
+    xo = x.clone().requires_grad_(True)
+    yo = mo.gcn_forward(osd, "g", xo, torch.from_numpy(arrays.edge_index), torch.from_numpy(arrays.edge_type),
+                        torch.from_numpy(arrays.edge_dist), mo.Ctx(training=True))
+    yo.backward(gy)
+    torch.testing.assert_close(y_s, yo.detach(), **TOL)
+    torch.testing.assert_close(gx_s, xo.grad, rtol=1e-4, atol=1e-5)
+    for k in ("layers.0.weight", "layers.1.root", "layers.0.nn.weight", "norm_layers.1.module.weight"):
+        want = osd["g." + k].grad
+        torch.testing.assert_close(g_s[k], want, rtol=1e-4, atol=1e-5 * max(1.0, float(want.abs().max())), msg=k)
+
+
+def test_structured_layout_bf16_and_dropout(cuda):
+    """bf16 mode + GCL dropout 0.1 through the structured layout: same dropout decisions as the generic layout
+    (they are keyed by the original edge id), results equal to bf16 round-off."""
+    from polyphemus_b200 import ops
+    import polyphemus_b200.ops as ops_mod
+    import itertools
+
+    gcn, sd, graph, arrays, x, gy = _structured_case(cuda, precision="bf16", p_gcl=0.1, seed=3)
+    outs = []
+    try:
+        for flag in (True, False):
+            ops.set_structured(flag)
+            gcn.load_state_dict(sd)
+            torch.manual_seed(11)
+            ops_mod._seed_counter = itertools.count()          # same per-layer dropout seeds in both runs
+            outs.append(_run_gcn(gcn, graph, x, gy, cuda))
+    finally:
+        ops.set_structured(True)
+    (y_s, gx_s, g_s, _), (y_g, gx_g, g_g, _) = outs
+    assert (y_s - y_g).abs().max() / y_g.abs().max() < 2e-2
+    assert (gx_s - gx_g).abs().max() / gx_g.abs().max() < 3e-2
+    for k in ("layers.0.weight", "layers.1.root", "layers.0.nn.weight"):
+        a, b = g_s[k].flatten().double(), g_g[k].flatten().double()
+        assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 0.999, k
