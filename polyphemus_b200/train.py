@@ -21,7 +21,7 @@ import torch.distributed as dist
 import torch.nn.functional as F
 
 from .graph import Graph, graphs_from_tensor
-from .vae import MAX_SIMU_TOKENS, N_DUR_TOKENS, N_PITCH_TOKENS
+from .vae import MAX_SIMU_TOKENS, N_DUR_TOKENS, N_PITCH_TOKENS, LogitParts
 
 PITCH_SOS, PITCH_EOS, PITCH_PAD = 128, 129, 130
 DUR_SOS, DUR_EOS, DUR_PAD = 96, 97, 98
@@ -30,8 +30,12 @@ DUR_SOS, DUR_EOS, DUR_PAD = 96, 97, 98
 def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float = 0.0, c_tokens=None):
     """Total loss and its parts (tensors). ``c_tokens`` int [N,16,2], when given, replaces the argmax over
     the one-hot ``c_tensor`` (same targets, no N x 15 x 230 read)."""
-    parts = getattr(c_logits, "_parts", None)
-    if parts is not None:
+    lazy = isinstance(c_logits, LogitParts)
+    parts = None if lazy else getattr(c_logits, "_parts", None)
+    if lazy:
+        pitch_logits = None
+        dur_logits = c_logits.dur.reshape(-1, c_logits.dur.size(-1)).float()
+    elif parts is not None:
         pitch_logits, dur_logits = (p.reshape(-1, p.size(-1)).float() for p in parts)
     else:
         logits = c_logits.reshape(-1, c_logits.size(-1)).float()
@@ -46,19 +50,31 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     # training.py:307 overwrites the structure logits with the structure tensor itself
     s_as_logits = s_tensor.reshape(-1, *s_logits.shape[2:]).float()
     s_loss = F.binary_cross_entropy_with_logits(s_as_logits.reshape(-1), s_tensor.reshape(-1).float())
-    pitch_loss = _masked_ce(pitch_logits, pitch_true, PITCH_PAD)
+    if lazy:   # per-row NLL under both pitch heads, the node's own head picked afterwards (N*15 scalars, not logits)
+        t = c_logits.drums.size(1)
+        rows_drum = c_logits.is_drum.repeat_interleave(t)
+        pitch_loss = _masked_ce((c_logits.drums.reshape(-1, c_logits.drums.size(-1)).float(),
+                                 c_logits.others.reshape(-1, c_logits.others.size(-1)).float()), pitch_true, PITCH_PAD,
+                                select=rows_drum)
+    else:
+        pitch_loss = _masked_ce(pitch_logits, pitch_true, PITCH_PAD)
     dur_loss = _masked_ce(dur_logits, dur_true, DUR_PAD)
     kld = (-0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp(), dim=1)).mean()
     total = pitch_loss + dur_loss + s_loss + beta * kld
     return total, {"pitch": pitch_loss, "dur": dur_loss, "structure": s_loss, "kld": kld}
 
 
-def _masked_ce(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
+def _masked_ce(logits, target: torch.Tensor, ignore_index: int, select: Optional[torch.Tensor] = None) -> torch.Tensor:
     """nn.CrossEntropyLoss(ignore_index=...) (training.py:100-101): mean over the non-ignored rows of
     -log_softmax(logits)[target]. Written out because the library's nll_loss reduction runs in a single block and
     costs milliseconds on 2M rows (the fused log_softmax kernel is fine)."""
     keep = target != ignore_index
-    nll = -F.log_softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
+    if select is not None:     # logits = (rows where select, rows where ~select): pick the NLL per row
+        nll_a = -F.log_softmax(logits[0], dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
+        nll_b = -F.log_softmax(logits[1], dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
+        nll = torch.where(select, nll_a, nll_b)
+    else:
+        nll = -F.log_softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
     return (nll * keep).sum() / keep.sum()
 
 
@@ -210,6 +226,9 @@ class TrainStep:
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, fused=model_is_cuda(model))
         self.autocast_bf16 = autocast_bf16
         self.beta_kld = beta_kld
+        for m in model.modules():            # the step only needs the loss: keep the content logits as head outputs
+            if hasattr(m, "materialize_logits"):
+                m.materialize_logits = False
 
     def __call__(self, graph: Graph, noise: Optional[torch.Tensor] = None):
         self.reducer.zero_grad()

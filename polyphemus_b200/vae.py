@@ -186,7 +186,7 @@ class ContentEncoder(nn.Module):
         d_tab = self._bn_table(self.dur_emb, self.bn_dur, d_ids, self.training)
         if ops.get_precision() == "bf16":          # gather straight into the GEMM's operand dtype
             p_tab, d_tab = p_tab.to(torch.bfloat16), d_tab.to(torch.bfloat16)
-        tokens = torch.cat((F.embedding(p_ids, p_tab), F.embedding(d_ids, d_tab)), dim=-1).view(k, t * self.d)
+        tokens = torch.cat((ops.table_gather(p_tab, p_ids), ops.table_gather(d_tab, d_ids)), dim=-1).view(k, t * self.d)
         chord = ops.tc_linear(tokens, self.chord_encoder.weight, self.chord_encoder.bias)
         return self.dropout_layer(F.relu(chord))
 
@@ -278,6 +278,7 @@ class ContentDecoder(nn.Module):
         self.non_drums_pitch_emb = nn.Linear(d // 2, N_PITCH_TOKENS)
         self.dur_emb = nn.Linear(d // 2, N_DUR_TOKENS)
         self.dropout_layer = nn.Dropout(p=self.dropout)
+        self.materialize_logits = True      # False: return LogitParts (loss-only consumers, see train.TrainStep)
 
     def forward(self, z_c, s):
         d, half = self.d, self.d // 2
@@ -303,8 +304,12 @@ class ContentDecoder(nn.Module):
             # zero weight rows and a -inf bias, so the padded logits vanish from every softmax downstream
             drums = _padded_head(self.drums_pitch_emb, h_pitch)
             others = _padded_head(self.non_drums_pitch_emb, h_pitch)
-            pitch_pad = torch.where(is_drum, drums, others)
             dur_pad = _padded_head(self.dur_emb, h_dur)
+            if not self.materialize_logits:
+                # training loops that only need the loss: skip assembling [N, 15, 230] (a select + a concatenation of
+                # GB-sized tensors and their backward); vae_losses selects per node at the level of the NLL instead
+                return LogitParts(drums, others, dur_pad, s.is_drum)
+            pitch_pad = torch.where(is_drum, drums, others)
             pitch, dur = pitch_pad[..., :N_PITCH_TOKENS], dur_pad[..., :N_DUR_TOKENS]
             c_logits = torch.cat((pitch, dur), dim=-1)
             c_logits._parts = (pitch_pad, dur_pad)   # lets the loss skip re-slicing (padding columns are -inf)
@@ -314,6 +319,19 @@ class ContentDecoder(nn.Module):
         c_logits = torch.cat((pitch, dur), dim=-1)
         c_logits._parts = (pitch, dur)          # lets the loss skip re-slicing the concatenation
         return c_logits
+
+
+class LogitParts:
+    """Content logits kept as the three head outputs (drum-pitch, non-drum-pitch, duration; width padded with -inf)
+    plus the per-node drum flag — what ``c_logits`` is assembled from. ``dense()`` builds the reference's
+    ``[N, 15, 230]`` tensor (model.py:571-576)."""
+
+    def __init__(self, drums, others, dur, is_drum):
+        self.drums, self.others, self.dur, self.is_drum = drums, others, dur, is_drum
+
+    def dense(self) -> torch.Tensor:
+        pitch = torch.where(self.is_drum.view(-1, 1, 1), self.drums, self.others)
+        return torch.cat((pitch[..., :N_PITCH_TOKENS], self.dur[..., :N_DUR_TOKENS]), dim=-1)
 
 
 def _padded_head(lin: nn.Linear, h: torch.Tensor) -> torch.Tensor:

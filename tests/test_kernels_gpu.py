@@ -395,3 +395,24 @@ def test_tensor_core_linear(cuda, precision, m, k, n):
     torch.testing.assert_close(x.grad.double(), x64.grad, **tol(x64.grad))
     torch.testing.assert_close(w.grad.double(), w64.grad, **tol(w64.grad))
     torch.testing.assert_close(b.grad.double(), b64.grad, **tol(b64.grad))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_table_gather_gradient(cuda, precision):
+    """ops.table_gather: gather from a tiny table, gradient through the split-K GEMM == index_add reference."""
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(5)
+    vocab, c, rows = 131, 128, 40000
+    table = torch.randn(vocab, c, generator=gen).to(cuda).requires_grad_(True)
+    ids = torch.randint(0, vocab, (rows // 8, 8), generator=gen).to(cuda)
+    ids[::3] = 130                                     # a very popular token (PAD)
+    g = torch.randn(rows // 8, 8, c, generator=gen).to(cuda)
+    out = ops.table_gather(table, ids, precision=precision)
+    assert torch.equal(out, table.detach()[ids])
+    out.backward(g)
+    ref = torch.zeros(vocab, c, dtype=torch.float64, device=cuda).index_add_(0, ids.reshape(-1), g.reshape(-1, c).double())
+    if precision == "fp32":
+        torch.testing.assert_close(table.grad.double(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+    else:
+        torch.testing.assert_close(table.grad.double(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))

@@ -183,7 +183,7 @@ def _vae_batch(ref, cuda):
     return device_batch(host, cuda, onehot=True)
 
 
-@pytest.mark.parametrize("content", ["token_ids", "onehot"])
+@pytest.mark.parametrize("content", ["token_ids", "onehot", "token_ids_lazy_logits"])
 def test_vae_training_step_matches_reference_golden(cuda, content):
     """Whole drop-in surface: VAE(graph) -> ((s_logits, c_logits), mu, log_var), reference loss, all gradients,
     BatchNorm running statistics; inputs go through the device graph builder (one empty bar included).
@@ -200,14 +200,20 @@ def test_vae_training_step_matches_reference_golden(cuda, content):
         tokens = graph.c_tokens
         if content == "onehot":
             graph.c_tokens = None
+        if content == "token_ids_lazy_logits":       # what train.TrainStep does: loss straight from the head outputs
+            vae.decoder.c_decoder.materialize_logits = False
         (s_logits, c_logits), mu, log_var = vae(graph, noise=_t(ref["noise"], cuda))
+        c_parts = c_logits
+        if content == "token_ids_lazy_logits":
+            assert isinstance(c_logits, pb.vae.LogitParts)
+            c_logits = c_parts.dense()
         # mu / log_var sit behind a BatchNorm over a batch of 4 sequences: reference self-noise level
         torch.testing.assert_close(mu.detach().cpu(), torch.from_numpy(ref["mu"]), rtol=1e-4, atol=2e-5)
         torch.testing.assert_close(log_var.detach().cpu(), torch.from_numpy(ref["log_var"]), rtol=1e-4, atol=2e-5)
         torch.testing.assert_close(s_logits.detach().cpu(), torch.from_numpy(ref["s_logits"]), **TOL)
         torch.testing.assert_close(c_logits.detach().cpu(), torch.from_numpy(ref["c_logits"]), rtol=1e-4, atol=2e-5)
         for use_tokens in (False, True):
-            loss, parts = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_logits, mu, log_var, beta=0.0,
+            loss, parts = vae_losses(graph.s_tensor, s_logits, graph.c_tensor, c_parts, mu, log_var, beta=0.0,
                                      c_tokens=tokens if use_tokens else None)
             assert abs(float(loss) - float(ref["loss"])) <= 1e-4 * abs(float(ref["loss"]))
         got_parts = torch.stack([parts[k] for k in ("pitch", "dur", "structure", "kld")]).detach().cpu()
