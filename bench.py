@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the second (host-fed) timed region")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="bracket the first timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--gcl-dropout", type=float, default=0.1, help="GCL message dropout (hard-wired 0.1 in the reference)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -280,7 +282,11 @@ def main():
     _ffi.profiler.reset()
     _ffi.profiler.enabled = True
     launches0 = _ffi.launch_counter["n"]
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     total_ms = timed(step_resident, args.steps)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     launches = _ffi.launch_counter["n"] - launches0
     _ffi.profiler.enabled = False
     summary = _ffi.profiler.summary()

@@ -131,6 +131,10 @@ typedef struct pb_csr {
   const int32_t* dist_perm;
   const void* dist_items;
   const int32_t* dist_item_ptr;
+  /* optional visiting order of the n_nodes rows (NULL = 0..n-1). The structured layout stores nodes sorted by
+   * track relation but visits them bar by bar, so that a bar's rows (spread over the four groups) are gathered
+   * while they are still in L2. */
+  const int32_t* node_order;
 } pb_csr_t;
 
 size_t pb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t n_relations);

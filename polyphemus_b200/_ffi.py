@@ -29,6 +29,7 @@ class CsrStruct(Structure):
         ("n_nodes", c_int64), ("n_edges", c_int64), ("n_relations", c_int32), ("reserved", c_int32),
         ("in_ptr", c_void_p), ("in_edge", c_void_p), ("in_eid", c_void_p), ("out_ptr", c_void_p),
         ("out_rec", c_void_p), ("dist_perm", c_void_p), ("dist_items", c_void_p), ("dist_item_ptr", c_void_p),
+        ("node_order", c_void_p),
     ]
 
 
@@ -104,7 +105,7 @@ def lib() -> ctypes.CDLL:
 # host-only queries are not counted).
 LAUNCHES = {
     "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
-    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
+    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2,

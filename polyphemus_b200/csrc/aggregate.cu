@@ -23,27 +23,36 @@ __global__ void edge_table_fwd_kernel(const float* __restrict__ w, const float* 
 }
 
 // partials [PB_DIST_ITEMS][d] (one row per work item, items of distance k = [item_ptr[k], item_ptr[k+1])) ->
-// g_w [d][32], g_b [d]; fixed summation order (item ascending, then k ascending)
-__global__ void __launch_bounds__(1024) edge_table_bwd_kernel(const float* __restrict__ partials,
-                                                              const int* __restrict__ item_ptr, int d,
-                                                              float* __restrict__ g_w, float* __restrict__ g_b) {
-  __shared__ float tile[32][33];
-  const int ci = threadIdx.x, k = threadIdx.y;
+// g_w [d][32], g_b [d]. Grid (d/32, 32 distances); block = 32 channels x 8 item-lanes: lane j adds items
+// i0+j, i0+j+8, ... and the 8 lanes are combined in fixed order -> deterministic. g_b is finished by a second
+// tiny kernel that adds the 32 distances of g_w in order.
+__global__ void __launch_bounds__(256) edge_table_bwd_kernel(const float* __restrict__ partials,
+                                                             const int* __restrict__ item_ptr, int d,
+                                                             float* __restrict__ g_w) {
+  __shared__ float red[8][33];
+  const int ci = threadIdx.x, j = threadIdx.y, k = blockIdx.y;
   const int c = blockIdx.x * 32 + ci;
+  const int i0 = __ldg(item_ptr + k), i1 = __ldg(item_ptr + k + 1);
   float s = 0.f;
-  if (c < d) {
-    const int i0 = __ldg(item_ptr + k), i1 = __ldg(item_ptr + k + 1);
-    for (int i = i0; i < i1; ++i) s += partials[(size_t)i * d + c];
-    g_w[(size_t)c * PB_N_DISTS + k] = s;
-  }
-  tile[k][ci] = s;
+  if (c < d)
+    for (int i = i0 + j; i < i1; i += 8) s += partials[(size_t)i * d + c];
+  red[j][ci] = s;
   __syncthreads();
-  if (k == 0 && c < d) {
+  if (j == 0 && c < d) {
     float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) t += tile[j][ci];
-    g_b[c] = t;
+    for (int q = 0; q < 8; ++q) t += red[q][ci];
+    g_w[(size_t)c * PB_N_DISTS + k] = t;
   }
+}
+
+__global__ void edge_table_bias_kernel(const float* __restrict__ g_w, int d, float* __restrict__ g_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < PB_N_DISTS; ++k) t += g_w[(size_t)c * PB_N_DISTS + k];
+  g_b[c] = t;
 }
 
 // ---------------------------------------------------------------------------------------------- dropout bits
@@ -121,13 +130,15 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
                                                       const int* __restrict__ in_eid, const float* __restrict__ x,
                                                       const float* __restrict__ table, void* __restrict__ a_hi,
                                                       void* __restrict__ a_lo, int64_t lda, int64_t n_nodes, int d,
-                                                      int n_rel, const uint16_t* __restrict__ keep_bits, float keep_scale) {
+                                                      int n_rel, const uint16_t* __restrict__ keep_bits, float keep_scale,
+                                                      const int* __restrict__ node_order) {
   constexpr uint32_t kFull = 0xffffffffu;
   constexpr int G16 = (CPL + 3) / 4;
   const int lane = threadIdx.x & 31;
   const int nchunk = d >> 2;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; v < n_nodes; v += n_warps) {
+  for (int64_t vi = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; vi < n_nodes; vi += n_warps) {
+    const int64_t v = node_order ? (int64_t)__ldg(node_order + vi) : vi;
     const size_t row = (size_t)v * lda;
     const int my_ptr = lane <= n_rel ? __ldg(in_ptr + v * n_rel + lane) : 0;
     const int beg_all = __shfl_sync(kFull, my_ptr, 0);
@@ -222,13 +233,14 @@ __global__ void __launch_bounds__(256) agg_bwd_dx_kernel(
     const int* __restrict__ out_ptr, const int4* __restrict__ out_rec, const float* __restrict__ x,
     const float* __restrict__ table, const void* __restrict__ d_a, int64_t ldda, const float* __restrict__ gy_res,
     float* __restrict__ gx, void* __restrict__ q_buf, int64_t n_nodes, int d, int n_rel,
-    const uint16_t* __restrict__ keep_bits, float keep_scale) {
+    const uint16_t* __restrict__ keep_bits, float keep_scale, const int* __restrict__ node_order) {
   constexpr uint32_t kFull = 0xffffffffu;
   constexpr int G16 = (CPL + 3) / 4;
   const int lane = threadIdx.x & 31;
   const int nchunk = d >> 2;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n_nodes; u += n_warps) {
+  for (int64_t ui = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; ui < n_nodes; ui += n_warps) {
+    const int64_t u = node_order ? (int64_t)__ldg(node_order + ui) : ui;
     const int my_ptr = lane < 2 ? __ldg(out_ptr + u + lane) : 0;
     const int beg = __shfl_sync(kFull, my_ptr, 0), end = __shfl_sync(kFull, my_ptr, 1);
     int base = beg;
@@ -351,8 +363,10 @@ extern "C" int pb_edge_table_fwd(const float* nn_weight, const float* nn_bias, i
 extern "C" int pb_edge_table_bwd(const float* dtable_partials, const int32_t* dist_item_ptr, int32_t d,
                                  float* g_nn_weight, float* g_nn_bias, pb_stream_t stream) {
   PB_REQUIRE(dtable_partials && dist_item_ptr && g_nn_weight && g_nn_bias && d > 0, "pb_edge_table_bwd: bad arguments");
-  edge_table_bwd_kernel<<<(d + 31) / 32, dim3(32, 32), 0, as_stream(stream)>>>(dtable_partials, dist_item_ptr, d,
-                                                                               g_nn_weight, g_nn_bias);
+  edge_table_bwd_kernel<<<dim3((d + 31) / 32, PB_N_DISTS), dim3(32, 8), 0, as_stream(stream)>>>(
+      dtable_partials, dist_item_ptr, d, g_nn_weight);
+  PB_LAUNCH_CHECK();
+  edge_table_bias_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(g_nn_weight, d, g_nn_bias);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
@@ -389,7 +403,8 @@ static int launch_agg_fwd(const pb_csr_t* g, const float* x, int d, const float*
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8 * 4));
 #define PB_AGG_FWD(CPL, EX)                                                                                      \
   agg_fwd_kernel<BF16, DROP, CPL, EX><<<grid, threads, 0, st>>>(g->in_ptr, g->in_edge, g->in_eid, x, table, a_hi, \
-                                                                a_lo, lda, g->n_nodes, d, g->n_relations, bits, scale)
+                                                                a_lo, lda, g->n_nodes, d, g->n_relations, bits, scale, \
+                                                                g->node_order)
   if (exact) {
     if (cpl == 1) PB_AGG_FWD(1, true);
     else if (cpl == 2) PB_AGG_FWD(2, true);
@@ -438,7 +453,8 @@ static int launch_agg_bwd(const pb_csr_t* g, const float* x, int d, const float*
   const int4* recs = reinterpret_cast<const int4*>(g->out_rec);
 #define PB_AGG_BWD(CPL, EX)                                                                                        \
   agg_bwd_dx_kernel<BF16, DROP, CPL, EX><<<grid, threads, 0, st>>>(g->out_ptr, recs, x, table, d_a, ldda, gy_res,   \
-                                                                   gx, q_buf, g->n_nodes, d, g->n_relations, bits, scale)
+                                                                   gx, q_buf, g->n_nodes, d, g->n_relations, bits, scale, \
+                                                                   g->node_order)
   if (exact) {
     if (cpl == 1) PB_AGG_BWD(1, true);
     else if (cpl == 2) PB_AGG_BWD(2, true);

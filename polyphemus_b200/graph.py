@@ -57,7 +57,14 @@ class CsrPlan:
         self.struct = _ffi.CsrStruct(n, e, r, 0, self.in_ptr.data_ptr(), self.in_edge.data_ptr(),
                                      self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr(),
                                      self.dist_perm.data_ptr(), self.dist_items.data_ptr(),
-                                     self.dist_item_ptr.data_ptr())
+                                     self.dist_item_ptr.data_ptr(), None)
+        self.node_order = None
+
+    def set_node_order(self, order: torch.Tensor) -> None:
+        """Visit the rows in `order` (int32 permutation of 0..n_nodes-1) instead of 0..n-1 (see pb_csr_t)."""
+        assert order.dtype == torch.int32 and order.numel() == self.n_nodes
+        self.node_order = order.contiguous()
+        self.struct.node_order = self.node_order.data_ptr()
 
     def ref(self):
         return ctypes.byref(self.struct)
@@ -92,6 +99,11 @@ class StructuredPlan:
         self.pos = torch.empty(n, dtype=torch.int64, device=dev).index_copy_(0, order, pos_sorted)  # node -> padded row
         slot = (graph.edge_type.to(torch.int16) - 3).clamp_(min=0).to(torch.uint8)   # track rels -> 0, onset 1, next 2
         self.plan = CsrPlan(self.pos[graph.edge_index], slot, graph.edge_dist, self.n_padded, n_relations=3)
+        # visit the rows bar by bar (original node order), the padding rows last: a bar's rows live in four distant
+        # group regions, touching them together keeps every gathered row in L2 until its last use
+        is_pad = torch.ones(self.n_padded, dtype=torch.bool, device=dev).index_fill_(0, self.pos, False)
+        pads = torch.arange(self.n_padded, device=dev)[is_pad] if self.n_padded > n else self.pos[:0]
+        self.plan.set_node_order(torch.cat((self.pos, pads)).to(torch.int32))
         self.groups = _ffi.GroupsStruct(4, 0, (ctypes.c_int64 * 4)(*starts), (ctypes.c_int64 * 4)(*counts))
 
     def groups_ref(self):

@@ -97,8 +97,27 @@ class GlobalAttention(nn.Module):
         self.gate_nn = gate_nn
         _reset(self.gate_nn)
 
+    def _gate(self, x):
+        """gate_nn(x); its trailing BatchNorm1d(1) over ~1e5 rows is done with plain reductions (the library's
+        single-channel BatchNorm kernels reduce in one block and cost ~0.5 ms each way)."""
+        nn_ = self.gate_nn
+        if not (isinstance(nn_, nn.Sequential) and len(nn_) == 2 and isinstance(nn_[1], nn.BatchNorm1d)
+                and nn_[1].num_features == 1 and nn_[1].training and nn_[1].track_running_stats):
+            return nn_(x)
+        bn = nn_[1]
+        g = nn_[0](x).float()
+        n = g.numel()
+        mean = g.mean()
+        var = (g - mean).square().mean()
+        with torch.no_grad():
+            m = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - m).add_(mean.detach().view(1), alpha=m)
+            bn.running_var.mul_(1 - m).add_((var.detach() * (n / max(n - 1, 1))).view(1), alpha=m)
+            bn.num_batches_tracked.add_(1)
+        return (g - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
+
     def forward(self, x, batch, size: int):
-        gate = self.gate_nn(x).view(-1, 1)
+        gate = self._gate(x).view(-1, 1)
         top = torch.full((size, 1), float("-inf"), dtype=gate.dtype, device=gate.device)
         top = top.scatter_reduce(0, batch.view(-1, 1), gate.detach(), reduce="amax", include_self=True)
         e = torch.exp(gate - top.index_select(0, batch))

@@ -1,0 +1,78 @@
+"""Turn the scratch ncu outputs in gpurun_out/ into the tracked summaries under profiles/ (run in the container).
+
+    python tools/summarize_profiles.py r01
+"""
+import collections
+import csv
+import glob
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio"]
+
+
+def launch_shares():
+    path = os.path.join(src, f"launches_{tag}.csv")
+    if not os.path.exists(path):
+        return
+    rows = list(csv.reader(open(path)))
+    start = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    hdr, data = rows[start], rows[start + 1:]
+    ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in data:
+        if len(r) <= vi:
+            continue
+        v = float(r[vi].replace(",", ""))
+        v = v / 1e3 if r[ui] == "ns" else v * 1e3 if r[ui] == "ms" else v
+        name = r[ki].split("(")[0][:80]
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    ours = sum(v[1] for k, v in agg.items() if "pb::" in k)
+    out = [f"# ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none  (bench.py --steps 1, LMD16, "
+           f"per-GPU batch 256, bf16): every launch of ONE timed step",
+           f"# {len(data)} launches, {tot / 1e3:.2f} ms serialised cold-cache device time; kernels of libpolyphemus_b200 (pb::*): "
+           f"{ours / 1e3:.2f} ms = {ours / tot:.1%}. Compare SHARES with bench.py's live CUDA-event numbers, not absolutes.",
+           "kernel,launches,total_us,share"]
+    for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:60]:
+        out.append(f"\"{k}\",{n},{t:.1f},{t / tot:.4f}")
+    open(os.path.join(dst, f"{tag}_launch_shares.csv"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out[:22]))
+
+
+def rep_summaries():
+    for rep in sorted(glob.glob(os.path.join(src, f"prof_*_{tag}.ncu-rep"))):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        idx = {h: i for i, h in enumerate(hdr)}
+        lines = [f"# ncu --set full --clock-control none --import-source on ({os.path.basename(rep)}); one row block per captured launch"]
+        for r in rows[2:]:
+            lines.append(f"kernel: {r[idx['Kernel Name']][:110]}")
+            for k in KEYS:
+                if k in idx and r[idx[k]] not in ("", "n/a"):
+                    lines.append(f"  {k:88s} {r[idx[k]][:24]:>24s} {units[idx[k]]}")
+        name = os.path.basename(rep).replace(".ncu-rep", ".txt").replace("prof_", f"{tag}_ncu_").replace(f"_{tag}.txt", ".txt")
+        open(os.path.join(dst, name), "w").write("\n".join(lines) + "\n")
+        print("wrote", name)
+
+
+launch_shares()
+rep_summaries()
