@@ -253,6 +253,23 @@ int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const flo
 int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d, int32_t dtype, void* g_hi, void* g_lo,
                  int64_t ldg, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Token cross entropy — replaces nn.CrossEntropyLoss(ignore_index=PAD) on the pitch / duration logits
+ * (training.py:100-101, 320-330) for logits kept per un-embedding head ([rows, classes], row stride ld, classes a
+ * multiple of 8 (PB_BF16) / 4 (PB_F32), at most 1024 / 512; padding columns hold -inf).
+ *   forward : nll[r] = logsumexp(logits[r]) - logits[r, target[r]],  lse[r] = logsumexp;  rows with
+ *             target == ignore_index are not read and give nll = lse = 0.
+ *   backward: grad[r, c] = (exp(logits[r,c] - lse[r]) - [c == target[r]]) * row_grad[r]   (0 for ignored rows),
+ *             written in the logits' own type.
+ * The mean over the kept rows is the caller's (sum(nll) / count), as is picking the drum / non-drum head per node
+ * (give each head the target with the other head's rows set to ignore_index).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_ce_fwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t classes, const int32_t* target,
+              int32_t ignore_index, float* nll, float* lse, pb_stream_t stream);
+int pb_ce_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t classes, const int32_t* target,
+              int32_t ignore_index, const float* lse, const float* row_grad, void* grad, int64_t ldg,
+              pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,6 +217,24 @@ __device__ __forceinline__ float4 load_grad4(const void* d_a, size_t elem_off) {
     return ldg4(reinterpret_cast<const float*>(d_a) + elem_off);
   }
 }
+template <bool BF16> struct GradRaw { using type = float4; };
+template <> struct GradRaw<true> { using type = uint2; };
+template <bool BF16>
+__device__ __forceinline__ typename GradRaw<BF16>::type load_grad_raw(const void* d_a, size_t elem_off) {
+  if constexpr (BF16)
+    return __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(d_a) + elem_off));
+  else
+    return ldg4(reinterpret_cast<const float*>(d_a) + elem_off);
+}
+template <bool BF16>
+__device__ __forceinline__ float4 unpack_grad_raw(typename GradRaw<BF16>::type p) {
+  if constexpr (BF16) {
+    const float2 a = unpack_bf16x2(p.x), b = unpack_bf16x2(p.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return p;
+  }
+}
 template <bool BF16>
 __device__ __forceinline__ void store_q(void* q, size_t elem_off, float4 v) {
   if constexpr (BF16)
@@ -229,7 +247,7 @@ __device__ __forceinline__ void store_q(void* q, size_t elem_off, float4 v) {
 // out-edges feed (same shape as the forward: coalesced record load, shuffles, 16-byte row gathers, full occupancy)
 // and emits, per out-edge position, the row q_e = ds_e * x[u] that the edge-table gradient needs.
 template <bool BF16, bool DROPOUT, int CPL, bool EXACT>
-__global__ void __launch_bounds__(256) agg_bwd_dx_kernel(
+__global__ void __launch_bounds__(256, (BF16 && CPL <= 4) ? 3 : 1) agg_bwd_dx_kernel(
     const int* __restrict__ out_ptr, const int4* __restrict__ out_rec, const float* __restrict__ x,
     const float* __restrict__ table, const void* __restrict__ d_a, int64_t ldda, const float* __restrict__ gy_res,
     float* __restrict__ gx, void* __restrict__ q_buf, int64_t n_nodes, int d, int n_rel,
@@ -258,22 +276,40 @@ __global__ void __launch_bounds__(256) agg_bwd_dx_kernel(
         }
       }
     }
-    for (int i = beg; i < end; ++i) {
+    // software pipeline over the out-edges: the gradient row and keep-bits of edge i+1 are in flight while edge i
+    // is consumed (a warp has ~3.5 out-edges; without this each one is a full DRAM round trip)
+    typename GradRaw<BF16>::type nraw[CPL];
+    uint32_t nkw[G16];
+    int nmeta = 0, ncnt = 0;
+    auto fetch = [&](int i) {
       if (i - base == 32) {  // warp-uniform (out-degree > 32 only)
         base = i;
         my_rec = base + lane < end ? __ldg(out_rec + base + lane) : make_int4(0, 0, 0, 0);
       }
       const int dst = __shfl_sync(kFull, my_rec.x, i - base);
-      const int meta = __shfl_sync(kFull, my_rec.y, i - base);
-      const int cnt = __shfl_sync(kFull, my_rec.w, i - base);
-      const size_t goff = (size_t)dst * ldda + (size_t)(meta & 0xff) * d + 4 * lane;
-      const float* trow = table + (size_t)(meta >> 8) * d + 4 * lane;
-      uint32_t kw[G16];
+      nmeta = __shfl_sync(kFull, my_rec.y, i - base);
+      ncnt = __shfl_sync(kFull, my_rec.w, i - base);
+      const size_t goff = (size_t)dst * ldda + (size_t)(nmeta & 0xff) * d + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        if (EXACT || lane + 32 * j < nchunk) nraw[j] = load_grad_raw<BF16>(d_a, goff + 128 * j);
       if constexpr (DROPOUT) {
         const uint32_t eid = (uint32_t)__shfl_sync(kFull, my_rec.z, i - base);
 #pragma unroll
-        for (int q = 0; q < G16; ++q) kw[q] = __ldg(keep_bits + ((size_t)eid * G16 + q) * 32 + lane);
+        for (int q = 0; q < G16; ++q) nkw[q] = __ldg(keep_bits + ((size_t)eid * G16 + q) * 32 + lane);
       }
+    };
+    if (beg < end) fetch(beg);
+    for (int i = beg; i < end; ++i) {
+      typename GradRaw<BF16>::type raw[CPL];
+      uint32_t kw[G16];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) raw[j] = nraw[j];
+#pragma unroll
+      for (int q = 0; q < G16; ++q) kw[q] = nkw[q];
+      const int meta = nmeta, cnt = ncnt;
+      if (i + 1 < end) fetch(i + 1);
+      const float* trow = table + (size_t)(meta >> 8) * d + 4 * lane;
       // d(mean)/d(sum) = 1/|segment| (one reciprocal per edge), times the dropout scale
       float coef = cnt > 1 ? 1.0f / (float)cnt : 1.0f;
       if constexpr (DROPOUT) coef *= keep_scale;
@@ -281,7 +317,7 @@ __global__ void __launch_bounds__(256) agg_bwd_dx_kernel(
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         if (EXACT || lane + 32 * j < nchunk) {
-          float4 ds = load_grad4<BF16>(d_a, goff + 128 * j);
+          float4 ds = unpack_grad_raw<BF16>(raw[j]);
           const float4 t = ldg4(trow + 128 * j);
           const float4 xv = xu[j];
           uint32_t nib = 0xFu;

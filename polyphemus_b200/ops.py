@@ -393,6 +393,44 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
 
 
+class TokenNllFn(torch.autograd.Function):
+    """Per-row negative log-likelihood of ``target`` under softmax(logits): pb_ce_fwd / pb_ce_bwd. Rows whose
+    target equals ``ignore_index`` give 0 and no gradient (nn.CrossEntropyLoss(ignore_index=...), training.py:100)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index: int):
+        rows, classes = logits.shape
+        dtype = _ffi.PB_BF16 if logits.dtype == torch.bfloat16 else _ffi.PB_F32
+        nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        with torch.cuda.device(logits.device):
+            _call("pb_ce_fwd", logits.data_ptr(), logits.stride(0), dtype, rows, classes, target.data_ptr(),
+                  int(ignore_index), nll.data_ptr(), lse.data_ptr(), _ffi.stream())
+        ctx.save_for_backward(logits, target, lse)
+        ctx.ignore_index, ctx.dtype = int(ignore_index), dtype
+        return nll
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, target, lse = ctx.saved_tensors
+        rows, classes = logits.shape
+        g = g.float().contiguous()
+        grad = torch.empty((rows, classes), dtype=logits.dtype, device=logits.device)
+        with torch.cuda.device(logits.device):
+            _call("pb_ce_bwd", logits.data_ptr(), logits.stride(0), ctx.dtype, rows, classes, target.data_ptr(),
+                  ctx.ignore_index, lse.data_ptr(), g.data_ptr(), grad.data_ptr(), classes, _ffi.stream())
+        return grad, None, None
+
+
+def token_nll(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
+    """nll f32 [rows] for CUDA logits [rows, classes] (bf16 or fp32, unit column stride) and int32 targets."""
+    if not (logits.is_cuda and logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float32)):
+        raise ValueError("token_nll needs 2-D CUDA bf16/fp32 logits with contiguous rows")
+    if target.dtype != torch.int32 or not target.is_contiguous() or target.numel() != logits.size(0):
+        raise ValueError("token_nll needs one contiguous int32 target per row")
+    return TokenNllFn.apply(logits, target, ignore_index)
+
+
 def dropout_keep_mask(n_edges: int, d: int, p_drop: float, seed: int, device) -> torch.Tensor:
     """The keep-mask pb_agg_fwd/bwd use for (seed, p): bool [E, d], indexed by edge_index column."""
     keep = torch.empty((n_edges, d), dtype=torch.uint8, device=device)

@@ -20,6 +20,7 @@ import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import ops
 from .graph import Graph, graphs_from_tensor
 from .vae import MAX_SIMU_TOKENS, N_DUR_TOKENS, N_PITCH_TOKENS, LogitParts
 
@@ -33,8 +34,7 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     lazy = isinstance(c_logits, LogitParts)
     parts = None if lazy else getattr(c_logits, "_parts", None)
     if lazy:
-        pitch_logits = None
-        dur_logits = c_logits.dur.reshape(-1, c_logits.dur.size(-1)).float()
+        pitch_logits = dur_logits = None
     elif parts is not None:
         pitch_logits, dur_logits = (p.reshape(-1, p.size(-1)).float() for p in parts)
     else:
@@ -50,31 +50,32 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     # training.py:307 overwrites the structure logits with the structure tensor itself
     s_as_logits = s_tensor.reshape(-1, *s_logits.shape[2:]).float()
     s_loss = F.binary_cross_entropy_with_logits(s_as_logits.reshape(-1), s_tensor.reshape(-1).float())
-    if lazy:   # per-row NLL under both pitch heads, the node's own head picked afterwards (N*15 scalars, not logits)
+    if lazy:
+        # fused row-wise cross entropy on the three head outputs (pb_ce_fwd/bwd): the node's own pitch head is picked
+        # by giving each head the targets with the other head's rows set to the ignored PAD id
         t = c_logits.drums.size(1)
         rows_drum = c_logits.is_drum.repeat_interleave(t)
-        pitch_loss = _masked_ce((c_logits.drums.reshape(-1, c_logits.drums.size(-1)).float(),
-                                 c_logits.others.reshape(-1, c_logits.others.size(-1)).float()), pitch_true, PITCH_PAD,
-                                select=rows_drum)
+        pitch_t, dur_t = pitch_true.int(), dur_true.int().contiguous()
+        pad = torch.full_like(pitch_t, PITCH_PAD)
+        flat = lambda x: x.reshape(-1, x.size(-1))
+        pitch_nll = (ops.token_nll(flat(c_logits.drums), torch.where(rows_drum, pitch_t, pad), PITCH_PAD).sum()
+                     + ops.token_nll(flat(c_logits.others), torch.where(rows_drum, pad, pitch_t), PITCH_PAD).sum())
+        pitch_loss = pitch_nll / (pitch_t != PITCH_PAD).sum()
+        dur_loss = ops.token_nll(flat(c_logits.dur), dur_t, DUR_PAD).sum() / (dur_t != DUR_PAD).sum()
     else:
         pitch_loss = _masked_ce(pitch_logits, pitch_true, PITCH_PAD)
-    dur_loss = _masked_ce(dur_logits, dur_true, DUR_PAD)
+        dur_loss = _masked_ce(dur_logits, dur_true, DUR_PAD)
     kld = (-0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp(), dim=1)).mean()
     total = pitch_loss + dur_loss + s_loss + beta * kld
     return total, {"pitch": pitch_loss, "dur": dur_loss, "structure": s_loss, "kld": kld}
 
 
-def _masked_ce(logits, target: torch.Tensor, ignore_index: int, select: Optional[torch.Tensor] = None) -> torch.Tensor:
+def _masked_ce(logits, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
     """nn.CrossEntropyLoss(ignore_index=...) (training.py:100-101): mean over the non-ignored rows of
     -log_softmax(logits)[target]. Written out because the library's nll_loss reduction runs in a single block and
-    costs milliseconds on 2M rows (the fused log_softmax kernel is fine)."""
+    costs milliseconds on 2M rows."""
     keep = target != ignore_index
-    if select is not None:     # logits = (rows where select, rows where ~select): pick the NLL per row
-        nll_a = -F.log_softmax(logits[0], dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
-        nll_b = -F.log_softmax(logits[1], dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
-        nll = torch.where(select, nll_a, nll_b)
-    else:
-        nll = -F.log_softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
+    nll = -F.log_softmax(logits, dim=1).gather(1, target.unsqueeze(1)).squeeze(1)
     return (nll * keep).sum() / keep.sum()
 
 

@@ -321,9 +321,10 @@ class ContentDecoder(nn.Module):
         if h.is_cuda:
             # un-embedding heads (131 / 99 outputs) on the tcgen05 GEMM: output width padded to a multiple of 64 with
             # zero weight rows and a -inf bias, so the padded logits vanish from every softmax downstream
-            drums = _padded_head(self.drums_pitch_emb, h_pitch)
-            others = _padded_head(self.non_drums_pitch_emb, h_pitch)
-            dur_pad = _padded_head(self.dur_emb, h_dur)
+            lazy_bf16 = bf16 and not self.materialize_logits    # loss-only: bf16 logits, as under autocast
+            drums = _padded_head(self.drums_pitch_emb, h_pitch, lazy_bf16)
+            others = _padded_head(self.non_drums_pitch_emb, h_pitch, lazy_bf16)
+            dur_pad = _padded_head(self.dur_emb, h_dur, lazy_bf16)
             if not self.materialize_logits:
                 # training loops that only need the loss: skip assembling [N, 15, 230] (a select + a concatenation of
                 # GB-sized tensors and their backward); vae_losses selects per node at the level of the NLL instead
@@ -350,16 +351,16 @@ class LogitParts:
 
     def dense(self) -> torch.Tensor:
         pitch = torch.where(self.is_drum.view(-1, 1, 1), self.drums, self.others)
-        return torch.cat((pitch[..., :N_PITCH_TOKENS], self.dur[..., :N_DUR_TOKENS]), dim=-1)
+        return torch.cat((pitch[..., :N_PITCH_TOKENS], self.dur[..., :N_DUR_TOKENS]), dim=-1).float()
 
 
-def _padded_head(lin: nn.Linear, h: torch.Tensor) -> torch.Tensor:
-    """lin(h) for h [n, t, k] with the output width padded up to a multiple of 64: [n, t, n_pad] fp32, padding = -inf."""
+def _padded_head(lin: nn.Linear, h: torch.Tensor, out_bf16: bool = False) -> torch.Tensor:
+    """lin(h) for h [n, t, k] with the output width padded up to a multiple of 64: [n, t, n_pad], padding = -inf."""
     n_out, k = lin.weight.shape
     pad = (-n_out) % 64
     w = F.pad(lin.weight, (0, 0, 0, pad))
     b = F.pad(lin.bias, (0, pad), value=float("-inf"))
-    out = ops.tc_linear(h.reshape(-1, k), w, b)
+    out = ops.tc_linear(h.reshape(-1, k), w, b, out_bf16=out_bf16)
     return out.view(*h.shape[:-1], n_out + pad)
 
 

@@ -416,3 +416,39 @@ def test_table_gather_gradient(cuda, precision):
         torch.testing.assert_close(table.grad.double(), ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
     else:
         torch.testing.assert_close(table.grad.double(), ref, rtol=2e-2, atol=2e-2 * float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("classes,valid", [(192, 131), (128, 99), (64, 64), (320, 300), (512, 512)])
+def test_token_nll_matches_cross_entropy(cuda, dtype, classes, valid):
+    """ops.token_nll (pb_ce_fwd / pb_ce_bwd) == F.cross_entropy(reduction='none', ignore_index) in fp64 on the same
+    (type-rounded) logits, -inf padding columns included; the gradient in the logits' own type."""
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(classes)
+    rows, ignore = 10007, valid - 1
+    logits = (4.0 * torch.randn(rows, classes, generator=gen)).to(dtype)
+    logits[:, valid:] = float("-inf")
+    target = torch.randint(0, valid, (rows,), generator=gen)
+    target[::5] = ignore
+    row_grad = torch.randn(rows, generator=gen)
+    lg = logits.to(cuda).requires_grad_(True)
+    nll = ops.token_nll(lg, target.int().to(cuda), ignore)
+    nll.backward(row_grad.to(cuda))
+    ref_in = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, target, ignore_index=ignore, reduction="none")
+    ref.backward(row_grad.double())
+    torch.testing.assert_close(nll.cpu().double(), ref.detach(), rtol=1e-5, atol=1e-5)
+    assert lg.grad.dtype == dtype and torch.isfinite(lg.grad).all()
+    assert (lg.grad[::5] == 0).all() and (lg.grad[:, valid:] == 0).all()
+    tol = dict(rtol=1e-5, atol=1e-6) if dtype == torch.float32 else dict(rtol=8e-3, atol=1e-6)
+    torch.testing.assert_close(lg.grad.cpu().double(), ref_in.grad, **tol)
+
+
+def test_token_nll_rejects_bad_layout(cuda):
+    from polyphemus_b200 import PolyphemusB200Error, ops
+
+    with pytest.raises(PolyphemusB200Error):
+        ops.token_nll(torch.zeros(8, 131, device=cuda), torch.zeros(8, dtype=torch.int32, device=cuda), 130)
+    with pytest.raises(ValueError):
+        ops.token_nll(torch.zeros(8, 136, device=cuda), torch.zeros(8, dtype=torch.int64, device=cuda), 130)
