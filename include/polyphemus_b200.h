@@ -270,6 +270,26 @@ int pb_ce_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32
               int32_t ignore_index, const float* lse, const float* row_grad, void* grad, int64_t ldg,
               pb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Chord embedding — replaces ContentEncoder's token embedding + BatchNorm + chord_encoder Linear + ReLU
+ * (model.py:355-388). tokens int16 [n_nodes, tok_stride] hold (pitch id, duration id) pairs, slot t at
+ * tok_offset + 2t (the dataset's [N, 16, 2] layout with the SOS slot skipped: tok_stride 32, tok_offset 2).
+ * tables [2, n_slots, vocab, d] (f32 for PB_F32, bf16 for PB_BF16) is the folded map
+ *   T[set, t, token] = BN(emb)[token] @ W_chord[:, t, half]^T  (pitch tokens first, duration tokens from dur_off),
+ * set_id[v] != 0 selects the drum tables (tables[1]).
+ *   forward : chord[v] = relu(bias + sum_t T[set_v, t, pitch_vt] + T[set_v, t, dur_off + dur_vt])   f32 [n, d]
+ *   bwd_prep: operands of dT = onehot^T @ (g * 1[chord > 0]) for pb_rgcn_gemm_bwd_weight (m = n_nodes,
+ *             k = n_slots * vocab_padded, d = 2 d): onehot [n, n_slots * vocab_padded] (bf16 / f32, no low part),
+ *             gcat [n, 2 d] with the node's set selecting the column block (bf16, or the TF32 hi/lo pair).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_chord_embed_fwd(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots,
+                       const uint8_t* set_id, const void* tables, int32_t dtype, int32_t vocab, int32_t dur_off,
+                       int32_t d, const float* bias, float* chord, int64_t ldc, int64_t n_nodes, pb_stream_t stream);
+int pb_chord_embed_bwd_prep(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots,
+                            const uint8_t* set_id, int32_t dur_off, int32_t vocab_padded, int32_t d,
+                            const float* chord, int64_t ldc, const float* g, int64_t ldg, int32_t dtype, void* onehot,
+                            void* gcat_hi, void* gcat_lo, int64_t n_nodes, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

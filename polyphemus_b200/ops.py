@@ -393,6 +393,66 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
 
 
+class ChordEmbedFn(torch.autograd.Function):
+    """chord[v] = relu(bias + sum of the node's 30 folded-table rows): pb_chord_embed_fwd; the table gradient is
+    onehot^T @ (g * relu') on the split-K weight-gradient GEMM (pb_chord_embed_bwd_prep builds both operands)."""
+
+    @staticmethod
+    def forward(ctx, tables, bias, tokens, set_id, tok_offset: int, dur_off: int, dtype: int):
+        _, n_slots, vocab, d = tables.shape
+        n = tokens.size(0)
+        tab = (tables.to(torch.bfloat16) if dtype == _ffi.PB_BF16 else tables.float()).contiguous()
+        bias_f = bias.float().contiguous()
+        out = torch.empty((n, d), dtype=torch.float32, device=tables.device)
+        with torch.cuda.device(tables.device):
+            _call("pb_chord_embed_fwd", tokens.data_ptr(), tokens.stride(0), tok_offset, n_slots, set_id.data_ptr(),
+                  tab.data_ptr(), dtype, vocab, dur_off, d, bias_f.data_ptr(), out.data_ptr(), d, n, _ffi.stream())
+        ctx.save_for_backward(tokens, set_id, out)
+        ctx.cfg = (n_slots, vocab, d, tok_offset, dur_off, dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        tokens, set_id, out = ctx.saved_tensors
+        n_slots, vocab, d, tok_offset, dur_off, dtype = ctx.cfg
+        n, dev = tokens.size(0), g.device
+        bf16 = dtype == _ffi.PB_BF16
+        vp = (vocab + 63) // 64 * 64
+        kk = n_slots * vp
+        g = g.float().contiguous()
+        op_dtype = torch.bfloat16 if bf16 else torch.float32
+        onehot = torch.empty((n, kk), dtype=op_dtype, device=dev)
+        onehot_lo = None if bf16 else torch.zeros((n, kk), dtype=op_dtype, device=dev)      # 0/1 is exact in TF32
+        gcat_hi = torch.empty((n, 2 * d), dtype=op_dtype, device=dev)
+        gcat_lo = None if bf16 else torch.empty((n, 2 * d), dtype=op_dtype, device=dev)
+        d_t = torch.empty((kk, 2 * d), dtype=torch.float32, device=dev)
+        lib = _ffi.lib()
+        ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, 2 * d, kk)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            st = _ffi.stream()
+            _call("pb_chord_embed_bwd_prep", tokens.data_ptr(), tokens.stride(0), tok_offset, n_slots, set_id.data_ptr(),
+                  dur_off, vp, d, out.data_ptr(), d, g.data_ptr(), d, dtype, onehot.data_ptr(), gcat_hi.data_ptr(),
+                  _ffi.ptr(gcat_lo), n, st)
+            _call("pb_rgcn_gemm_bwd_weight", onehot.data_ptr(), _ffi.ptr(onehot_lo), kk, gcat_hi.data_ptr(),
+                  _ffi.ptr(gcat_lo), 2 * d, d_t.data_ptr(), n, 2 * d, kk, None, dtype, ws.data_ptr(), ws_bytes, st,
+                  tag="linear")
+        d_tables = d_t.view(n_slots, vp, 2, d)[:, :vocab].permute(2, 0, 1, 3)
+        d_bias = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=dev)).sum(0)
+        return d_tables, d_bias, None, None, None, None, None
+
+
+def chord_embed(tables: torch.Tensor, bias: torch.Tensor, tokens: torch.Tensor, set_id: torch.Tensor,
+                tok_offset: int, dur_off: int, precision: Optional[str] = None) -> torch.Tensor:
+    """Folded chord embedding (see csrc/chord.cu): tables f32 [2, n_slots, vocab, d], tokens int16 [N, stride] with
+    (pitch, duration) pairs from ``tok_offset``, set_id uint8/bool [N] (1 = drum tables) -> relu'd chords f32 [N, d]."""
+    if not (tables.is_cuda and tokens.dtype == torch.int16 and tokens.stride(-1) == 1 and set_id.is_contiguous()):
+        raise ValueError("chord_embed needs CUDA tables, int16 tokens with contiguous rows and a contiguous set flag")
+    tok2d = tokens.view(tokens.size(0), -1)
+    flags = set_id.view(torch.uint8) if set_id.dtype == torch.bool else set_id
+    return ChordEmbedFn.apply(tables, bias, tok2d, flags, tok_offset, dur_off, _PRECISIONS[precision or _default_precision])
+
+
 class TokenNllFn(torch.autograd.Function):
     """Per-row negative log-likelihood of ``target`` under softmax(logits): pb_ce_fwd / pb_ce_bwd. Rows whose
     target equals ``ignore_index`` give 0 and no gradient (nn.CrossEntropyLoss(ignore_index=...), training.py:100)."""
@@ -420,6 +480,63 @@ class TokenNllFn(torch.autograd.Function):
             _call("pb_ce_bwd", logits.data_ptr(), logits.stride(0), ctx.dtype, rows, classes, target.data_ptr(),
                   ctx.ignore_index, lse.data_ptr(), g.data_ptr(), grad.data_ptr(), classes, _ffi.stream())
         return grad, None, None
+
+
+class TokenNllSegmentsFn(torch.autograd.Function):
+    """TokenNllFn for several heads that share one logits matrix: head i owns the column block
+    [col0_i, col0_i + width_i) of ``logits`` [rows, cols] and has its own targets / ignored id. The blocks tile the
+    columns, so the backward fills ONE gradient matrix in place (no per-head slices to zero-fill and add up)."""
+
+    @staticmethod
+    def forward(ctx, logits, specs, *targets):
+        rows = logits.size(0)
+        dtype = _ffi.PB_BF16 if logits.dtype == torch.bfloat16 else _ffi.PB_F32
+        es = logits.element_size()
+        outs, lses = [], []
+        with torch.cuda.device(logits.device):
+            for (col0, width, ignore), target in zip(specs, targets):
+                nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
+                lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+                _call("pb_ce_fwd", logits.data_ptr() + col0 * es, logits.stride(0), dtype, rows, width, target.data_ptr(),
+                      int(ignore), nll.data_ptr(), lse.data_ptr(), _ffi.stream())
+                outs.append(nll)
+                lses.append(lse)
+        ctx.save_for_backward(logits, *targets, *lses)
+        ctx.specs, ctx.dtype = specs, dtype
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        n = len(ctx.specs)
+        logits, targets, lses = ctx.saved_tensors[0], ctx.saved_tensors[1:1 + n], ctx.saved_tensors[1 + n:]
+        rows, cols = logits.shape
+        es = logits.element_size()
+        grad = torch.empty((rows, cols), dtype=logits.dtype, device=logits.device)
+        with torch.cuda.device(logits.device):
+            for (col0, width, ignore), target, lse, g in zip(ctx.specs, targets, lses, gs):
+                g = torch.zeros(rows, dtype=torch.float32, device=logits.device) if g is None else g.float().contiguous()
+                _call("pb_ce_bwd", logits.data_ptr() + col0 * es, logits.stride(0), ctx.dtype, rows, width,
+                      target.data_ptr(), int(ignore), lse.data_ptr(), g.data_ptr(), grad.data_ptr() + col0 * es, cols,
+                      _ffi.stream())
+        return (grad, None) + (None,) * n
+
+
+def token_nll_segments(logits: torch.Tensor, segments) -> tuple:
+    """segments = [(col0, width, target int32 [rows], ignore_index), ...] tiling the columns of the CUDA ``logits``
+    [rows, cols] (bf16 / fp32, unit column stride) -> one nll f32 [rows] per segment."""
+    if not (logits.is_cuda and logits.dim() == 2 and logits.stride(1) == 1 and logits.dtype in (torch.bfloat16, torch.float32)):
+        raise ValueError("token_nll_segments needs 2-D CUDA bf16/fp32 logits with contiguous rows")
+    cover = 0
+    for col0, width, target, _ in segments:
+        if col0 != cover:
+            raise ValueError("segments must tile the columns in order")
+        if target.dtype != torch.int32 or not target.is_contiguous() or target.numel() != logits.size(0):
+            raise ValueError("token_nll_segments needs one contiguous int32 target per row and segment")
+        cover += width
+    if cover != logits.size(1):
+        raise ValueError(f"segments cover {cover} of {logits.size(1)} columns")
+    specs = tuple((int(c), int(w), int(i)) for c, w, _, i in segments)
+    return TokenNllSegmentsFn.apply(logits, specs, *[t for _, _, t, _ in segments])
 
 
 def token_nll(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> torch.Tensor:

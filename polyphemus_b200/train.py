@@ -58,10 +58,17 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
         pitch_t, dur_t = pitch_true.int(), dur_true.int().contiguous()
         pad = torch.full_like(pitch_t, PITCH_PAD)
         flat = lambda x: x.reshape(-1, x.size(-1))
-        pitch_nll = (ops.token_nll(flat(c_logits.drums), torch.where(rows_drum, pitch_t, pad), PITCH_PAD).sum()
-                     + ops.token_nll(flat(c_logits.others), torch.where(rows_drum, pad, pitch_t), PITCH_PAD).sum())
-        pitch_loss = pitch_nll / (pitch_t != PITCH_PAD).sum()
-        dur_loss = ops.token_nll(flat(c_logits.dur), dur_t, DUR_PAD).sum() / (dur_t != DUR_PAD).sum()
+        t_drum, t_other = torch.where(rows_drum, pitch_t, pad), torch.where(rows_drum, pad, pitch_t)
+        if c_logits.combined is not None:          # the heads are column blocks of one matrix: one gradient buffer
+            w0, w1, w2 = c_logits.widths
+            nll_drum, nll_other, nll_dur = ops.token_nll_segments(
+                flat(c_logits.combined), [(0, w0, t_drum, PITCH_PAD), (w0, w1, t_other, PITCH_PAD), (w0 + w1, w2, dur_t, DUR_PAD)])
+        else:
+            nll_drum = ops.token_nll(flat(c_logits.drums), t_drum, PITCH_PAD)
+            nll_other = ops.token_nll(flat(c_logits.others), t_other, PITCH_PAD)
+            nll_dur = ops.token_nll(flat(c_logits.dur), dur_t, DUR_PAD)
+        pitch_loss = (nll_drum.sum() + nll_other.sum()) / (pitch_t != PITCH_PAD).sum()
+        dur_loss = nll_dur.sum() / (dur_t != DUR_PAD).sum()
     else:
         pitch_loss = _masked_ce(pitch_logits, pitch_true, PITCH_PAD)
         dur_loss = _masked_ce(dur_logits, dur_true, DUR_PAD)

@@ -170,30 +170,68 @@ class ContentEncoder(nn.Module):
         return self.dropout_layer(F.relu(chord))
 
     @staticmethod
-    def _bn_table(emb: nn.Linear, bn: nn.BatchNorm1d, ids: torch.Tensor, training: bool) -> torch.Tensor:
+    def _bn_table(emb: nn.Linear, bn: nn.BatchNorm1d, ids: Optional[torch.Tensor], training: bool,
+                  counts: Optional[torch.Tensor] = None) -> torch.Tensor:
         """BatchNorm(Linear(one_hot(ids))) as a [vocab, c] table.
 
         A Linear applied to a one-hot row is a column of its weight plus the bias, so the rows BatchNorm sees
         take only `vocab` distinct values: its batch statistics are the histogram-weighted statistics of those
         values. Same function as model.py:357-362 / 369-376 (fp32 round-off aside), without materialising the
-        [N*15, 230] one-hot input or the [N*15, d/2] pre-norm activations.
+        [N*15, 230] one-hot input or the [N*15, d/2] pre-norm activations. ``counts`` (the token histogram, [vocab])
+        may be given instead of ``ids``; an empty histogram leaves the running statistics untouched.
         """
         table = emb.weight.float().t() + emb.bias.float()                       # [vocab, c]
         use_batch_stats = training or bn.running_mean is None
         if use_batch_stats:
-            n = ids.numel()
-            cnt = torch.bincount(ids.reshape(-1), minlength=table.size(0)).to(table.dtype)
+            if counts is None:
+                counts = torch.bincount(ids.reshape(-1), minlength=table.size(0))
+            cnt = counts.to(table.dtype)
+            n_true = cnt.sum()
+            n = n_true.clamp(min=1.0)
             mean = (cnt @ table) / n
             var = (cnt @ (table - mean).square()) / n                           # biased, as BatchNorm normalises
             if training and bn.running_mean is not None:
                 with torch.no_grad():
                     m = bn.momentum if bn.momentum is not None else 0.1
-                    bn.running_mean.mul_(1 - m).add_(mean.detach(), alpha=m)
-                    bn.running_var.mul_(1 - m).add_(var.detach() * (n / max(n - 1, 1)), alpha=m)
-                    bn.num_batches_tracked.add_(1)
+                    m_eff = m * (n_true > 0).to(table.dtype)
+                    unbiased = var.detach() * (n / (n - 1).clamp(min=1.0))
+                    bn.running_mean.add_(m_eff * (mean.detach() - bn.running_mean))
+                    bn.running_var.add_(m_eff * (unbiased - bn.running_var))
+                    bn.num_batches_tracked.add_((n_true > 0).to(bn.num_batches_tracked.dtype))
         else:
             mean, var = bn.running_mean.float(), bn.running_var.float()
         return (table - mean) * torch.rsqrt(var + bn.eps) * bn.weight.float() + bn.bias.float()
+
+    def _embed_folded(self, tokens: torch.Tensor, is_drum: torch.Tensor) -> torch.Tensor:
+        """tokens int16 [N, 16, 2], is_drum bool [N] -> relu'd chord embeddings f32 [N, d] in node order.
+
+        Everything between the token ids and chord_encoder's output is linear in the one-hot tokens (embedding,
+        BatchNorm with the statistics of `_bn_table`, concatenation, Linear), so it folds into a table
+        T[set, slot, token, :] = BN(emb)[token] @ W_chord[:, slot, half]^T — 2 x 15 x 230 rows built here from the live
+        parameters (autograd reaches them through the einsum) — and the chord is a 30-row gather-sum per node
+        (ops.chord_embed). Same function as model.py:355-388; drum / non-drum nodes pick their table set in place, so
+        there is no split, permutation or concatenation of node rows either."""
+        t, half, d = MAX_SIMU_TOKENS - 1, self.d // 2, self.d
+        with torch.autocast(device_type=tokens.device.type, enabled=False):
+            counts = (None, None)
+            if self.training:
+                ids = tokens[:, 1:, :].long()
+                sets = is_drum.long().view(-1, 1)
+                cnt_p = torch.bincount((ids[..., 0] + N_PITCH_TOKENS * sets).reshape(-1), minlength=2 * N_PITCH_TOKENS)
+                cnt_d = torch.bincount((ids[..., 1] + N_DUR_TOKENS * sets).reshape(-1), minlength=2 * N_DUR_TOKENS)
+                counts = (cnt_p.view(2, -1), cnt_d.view(2, -1))
+            pick = lambda c, i: None if c is None else c[i]
+            # the reference embeds the drum rows first, then the others (bn_dur's running statistics see both)
+            p_drum = self._bn_table(self.drums_pitch_emb, self.bn_drums, None, self.training, pick(counts[0], 1))
+            d_drum = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 1))
+            p_other = self._bn_table(self.non_drums_pitch_emb, self.bn_non_drums, None, self.training, pick(counts[0], 0))
+            d_other = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 0))
+            w = self.chord_encoder.weight.float().view(d, t, 2, half)             # [out, slot, pitch|dur, half]
+            t_pitch = torch.einsum("svh,oth->stvo", torch.stack((p_other, p_drum)), w[:, :, 0])
+            t_dur = torch.einsum("svh,oth->stvo", torch.stack((d_other, d_drum)), w[:, :, 1])
+            tables = torch.cat((t_pitch, t_dur), dim=2)                           # [2, 15, 230, d]
+            return ops.chord_embed(tables, self.chord_encoder.bias, tokens, is_drum, tok_offset=2,
+                                   dur_off=N_PITCH_TOKENS)
 
     def _embed_ids(self, ids, pitch_emb, pitch_bn):
         """ids int [k, 15, 2] (pitch id, duration id) -> chord embedding [k, d]; token-table form of `_embed`."""
@@ -210,19 +248,22 @@ class ContentEncoder(nn.Module):
         return self.dropout_layer(F.relu(chord))
 
     def forward(self, graph):
-        perm, n_drum = _drum_split(graph)
         ids = getattr(graph, "c_tokens", None)
-        if ids is not None:                                    # dataset layout: token ids (preprocess.py:210)
-            ids = ids[:, 1:, :]                                # drop SOS
-            drums = self._embed_ids(ids.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
-            others = self._embed_ids(ids.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
-        else:                                                  # reference layout: one-hot float c_tensor
-            c = graph.c_tensor[:, 1:, :]
-            drums = self._embed(c.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
-            others = self._embed(c.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
-        x = torch.empty((perm.numel(), self.d), dtype=drums.dtype, device=drums.device)
-        x = x.index_copy(0, perm, torch.cat((drums, others.to(drums.dtype)), dim=0))
-        graph.x = x.float()
+        if ids is not None and ids.is_cuda and ids.dtype == torch.int16 and ids.is_contiguous() and self.d % 4 == 0:
+            graph.x = self.dropout_layer(self._embed_folded(ids, graph.is_drum.contiguous()))
+        else:
+            perm, n_drum = _drum_split(graph)
+            if ids is not None:                                    # token ids off the accelerated path (CPU, int64)
+                ids = ids[:, 1:, :]                                # drop SOS
+                drums = self._embed_ids(ids.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
+                others = self._embed_ids(ids.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
+            else:                                                  # reference layout: one-hot float c_tensor
+                c = graph.c_tensor[:, 1:, :]
+                drums = self._embed(c.index_select(0, perm[:n_drum]), self.drums_pitch_emb, self.bn_drums)
+                others = self._embed(c.index_select(0, perm[n_drum:]), self.non_drums_pitch_emb, self.bn_non_drums)
+            x = torch.empty((perm.numel(), self.d), dtype=drums.dtype, device=drums.device)
+            x = x.index_copy(0, perm, torch.cat((drums, others.to(drums.dtype)), dim=0))
+            graph.x = x.float()
         graph.distinct_bars = graph.bars + self.n_bars * graph.batch
         h = self.graph_encoder(graph)
         n_seg = _n_segments(graph, self.n_bars)
@@ -312,6 +353,9 @@ class ContentDecoder(nn.Module):
         w = self.chord_decoder.weight.view(t, 2, half, d)
         b = self.chord_decoder.bias.view(t, 2, half)
         bf16 = ops.get_precision() == "bf16"
+        dropout_active = self.training and self.dropout_layer.p > 0
+        if h.is_cuda and not self.materialize_logits and not dropout_active and d % 64 == 0:
+            return self._folded_heads(h, w, b, s.is_drum, bf16)
         h_pitch = ops.tc_linear(h, w[:, 0].reshape(t * half, d), b[:, 0].reshape(-1), out_bf16=bf16)
         h_dur = ops.tc_linear(h, w[:, 1].reshape(t * half, d), b[:, 1].reshape(-1), out_bf16=bf16)
         h_pitch = self.dropout_layer(h_pitch).view(-1, t, half)
@@ -340,6 +384,34 @@ class ContentDecoder(nn.Module):
         c_logits._parts = (pitch, dur)          # lets the loss skip re-slicing the concatenation
         return c_logits
 
+    def _folded_heads(self, h, w, b, is_drum, bf16: bool) -> "LogitParts":
+        """With the dropout between chord_decoder and the un-embedding heads inactive (p = 0 as in training.json, or
+        eval) the two Linears compose: logits[n, t] = h[n] @ (W_head W_cd[t, half])^T + (W_head b_cd[t, half] + b_head).
+        One GEMM h [N, d] x [15 * 512, d]^T then yields, per token slot, [drum-pitch 192 | non-drum-pitch 192 |
+        duration 128] logits (131 / 131 / 99 real columns, the rest -inf) — same function as model.py:549-576 without
+        the [N, 15, d] intermediate or the three head GEMMs over N * 15 rows. Autograd reaches the four Linears through
+        the small composition einsums."""
+        t = w.size(0)
+        with torch.autocast(device_type=h.device.type, enabled=False):
+            blocks_w, blocks_b = [], []
+            for lin, which in ((self.drums_pitch_emb, 0), (self.non_drums_pitch_emb, 0), (self.dur_emb, 1)):
+                hw, hb = lin.weight.float(), lin.bias.float()
+                pad = (-hw.size(0)) % 64
+                wc = torch.einsum("ch,thd->tcd", hw, w[:, which].float())              # [t, C, d]
+                bc = torch.einsum("ch,th->tc", hw, b[:, which].float()) + hb           # [t, C]
+                blocks_w.append(F.pad(wc, (0, 0, 0, pad)))
+                blocks_b.append(F.pad(bc, (0, pad), value=float("-inf")))
+            widths = [x.size(1) for x in blocks_w]
+            w_all = torch.cat(blocks_w, dim=1)                                          # [t, 512, d]
+            b_all = torch.cat(blocks_b, dim=1)
+            cols = w_all.size(1)
+            out = ops.tc_linear(h.float(), w_all.view(t * cols, -1), b_all.view(-1), out_bf16=bf16)
+        out = out.view(-1, t, cols)
+        c0, c1 = widths[0], widths[0] + widths[1]
+        parts = LogitParts(out[..., :c0], out[..., c0:c1], out[..., c1:], is_drum)
+        parts.combined, parts.widths = out, widths
+        return parts
+
 
 class LogitParts:
     """Content logits kept as the three head outputs (drum-pitch, non-drum-pitch, duration; width padded with -inf)
@@ -348,6 +420,7 @@ class LogitParts:
 
     def __init__(self, drums, others, dur, is_drum):
         self.drums, self.others, self.dur, self.is_drum = drums, others, dur, is_drum
+        self.combined, self.widths = None, None     # set when the three heads are column blocks of one matrix
 
     def dense(self) -> torch.Tensor:
         pitch = torch.where(self.is_drum.view(-1, 1, 1), self.drums, self.others)

@@ -452,3 +452,42 @@ def test_token_nll_rejects_bad_layout(cuda):
         ops.token_nll(torch.zeros(8, 131, device=cuda), torch.zeros(8, dtype=torch.int32, device=cuda), 130)
     with pytest.raises(ValueError):
         ops.token_nll(torch.zeros(8, 136, device=cuda), torch.zeros(8, dtype=torch.int64, device=cuda), 130)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("d", [64, 192, 512])
+def test_chord_embed_matches_dense_formulation(cuda, precision, d):
+    """ops.chord_embed (pb_chord_embed_fwd / bwd_prep + split-K GEMM) == relu(bias + sum of table rows) written with
+    plain index arithmetic in fp64, and its autograd gradients for the tables and the bias."""
+    from polyphemus_b200 import ops
+    from polyphemus_b200.train import synthetic_tokens
+
+    gen = torch.Generator().manual_seed(d)
+    n, slots, vocab, dur_off = 3001, 15, 230, 131
+    tokens = synthetic_tokens(n, gen)                                  # int16 [n, 16, 2]
+    is_drum = torch.rand(n, generator=gen) < 0.3
+    tables = (0.2 * torch.randn(2, slots, vocab, d, generator=gen)).requires_grad_(True)
+    bias = (0.1 * torch.randn(d, generator=gen)).requires_grad_(True)
+    g = torch.randn(n, d, generator=gen)
+
+    t_dev = tables.detach().to(cuda).requires_grad_(True)
+    b_dev = bias.detach().to(cuda).requires_grad_(True)
+    out = ops.chord_embed(t_dev, b_dev, tokens.to(cuda), is_drum.to(cuda), tok_offset=2, dur_off=dur_off, precision=precision)
+    out.backward(g.to(cuda))
+
+    tab = tables.detach()
+    if precision == "bf16":
+        tab = tab.to(torch.bfloat16).float()                           # the forward gathers bf16 tables
+    tab = tab.double().requires_grad_(True)
+    bias64 = bias.detach().double().requires_grad_(True)
+    ids = tokens[:, 1:, :].long()
+    sets = is_drum.long().view(-1, 1).expand(-1, slots)
+    slot = torch.arange(slots).view(1, -1).expand(n, -1)
+    pre = bias64 + tab[sets, slot, ids[..., 0]].sum(1) + tab[sets, slot, dur_off + ids[..., 1]].sum(1)
+    ref = torch.relu(pre)
+    ref.backward(g.double())
+    torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=1e-5, atol=1e-5)
+    scale = float(tab.grad.abs().max())
+    tol = dict(rtol=1e-4, atol=1e-5 * scale) if precision == "fp32" else dict(rtol=2e-2, atol=2e-2 * scale)
+    torch.testing.assert_close(t_dev.grad.cpu().double(), tab.grad, **tol)
+    torch.testing.assert_close(b_dev.grad.cpu().double(), bias64.grad, rtol=1e-4, atol=1e-4 * float(bias64.grad.abs().max()))

@@ -183,7 +183,7 @@ def _vae_batch(ref, cuda):
     return device_batch(host, cuda, onehot=True)
 
 
-@pytest.mark.parametrize("content", ["token_ids", "onehot", "token_ids_lazy_logits"])
+@pytest.mark.parametrize("content", ["token_ids", "onehot", "token_ids_lazy_logits", "token_ids_lazy_unfolded"])
 def test_vae_training_step_matches_reference_golden(cuda, content):
     """Whole drop-in surface: VAE(graph) -> ((s_logits, c_logits), mu, log_var), reference loss, all gradients,
     BatchNorm running statistics; inputs go through the device graph builder (one empty bar included).
@@ -200,12 +200,17 @@ def test_vae_training_step_matches_reference_golden(cuda, content):
         tokens = graph.c_tokens
         if content == "onehot":
             graph.c_tokens = None
-        if content == "token_ids_lazy_logits":       # what train.TrainStep does: loss straight from the head outputs
+        if content.startswith("token_ids_lazy"):     # what train.TrainStep does: loss straight from the head outputs
             vae.decoder.c_decoder.materialize_logits = False
+        if content == "token_ids_lazy_unfolded":
+            # an active dropout between chord_decoder and the heads forbids composing them; p = 1e-12 keeps every
+            # element and scales by exactly 1.0f, so the separate-heads path must reproduce the same golden numbers
+            vae.decoder.c_decoder.dropout_layer.p = 1e-12
         (s_logits, c_logits), mu, log_var = vae(graph, noise=_t(ref["noise"], cuda))
         c_parts = c_logits
-        if content == "token_ids_lazy_logits":
+        if content.startswith("token_ids_lazy"):
             assert isinstance(c_logits, pb.vae.LogitParts)
+            assert (c_parts.combined is not None) == (content == "token_ids_lazy_logits")
             c_logits = c_parts.dense()
         # mu / log_var sit behind a BatchNorm over a batch of 4 sequences: reference self-noise level
         torch.testing.assert_close(mu.detach().cpu(), torch.from_numpy(ref["mu"]), rtol=1e-4, atol=2e-5)
