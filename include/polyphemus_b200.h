@@ -290,6 +290,22 @@ int pb_chord_embed_bwd_prep(const int16_t* tokens, int64_t tok_stride, int32_t t
                             const float* chord, int64_t ldc, const float* g, int64_t ldg, int32_t dtype, void* onehot,
                             void* gcat_hi, void* gcat_lo, int64_t n_nodes, pb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-bar segment operators. The nodes of bar b are rows bar_ptr[b] .. bar_ptr[b+1] (pb_graph_count's node_ptr; at most
+ * 128 per bar); one warp per bar, fixed summation order.
+ *   pb_bar_pool_*   — PyG GlobalAttention pooling (model.py:335-340, 409): alpha = softmax over the bar of gate,
+ *                     out[b] = sum_v alpha_v h[v];  backward gives g_h and g_gate from g_out.
+ *   pb_bar_expand_* — x[v] = z[bar(v)] (model.py:542-546) and its segment-sum gradient g_z[b] = sum_v g_x[v].
+ * ---------------------------------------------------------------------------------------------- */
+int pb_bar_pool_fwd(const float* h, int64_t ldh, const float* gate, const int32_t* bar_ptr, int64_t n_bars, int32_t d,
+                    float* alpha, float* out, pb_stream_t stream);
+int pb_bar_pool_bwd(const float* h, int64_t ldh, const float* alpha, const int32_t* bar_ptr, int64_t n_bars, int32_t d,
+                    const float* g_out, float* g_h, int64_t ldgh, float* g_gate, pb_stream_t stream);
+int pb_bar_expand_fwd(const float* z, const int32_t* bar_ptr, int64_t n_bars, int32_t d, float* x, int64_t ldx,
+                      pb_stream_t stream);
+int pb_bar_expand_bwd(const float* g_x, int64_t ldg, const int32_t* bar_ptr, int64_t n_bars, int32_t d, float* g_z,
+                      pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -81,6 +81,10 @@ SIGNATURES = {
                                    c_int64, _P]),
     "pb_chord_embed_bwd_prep": (c_int, [_P, c_int64, c_int32, c_int32, _P, c_int32, c_int32, c_int32, _P, c_int64, _P, c_int64,
                                         c_int32, _P, _P, _P, c_int64, _P]),
+    "pb_bar_pool_fwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, _P, _P, _P]),
+    "pb_bar_pool_bwd": (c_int, [_P, c_int64, _P, _P, c_int64, c_int32, _P, _P, c_int64, _P, _P]),
+    "pb_bar_expand_fwd": (c_int, [_P, _P, c_int64, c_int32, _P, c_int64, _P]),
+    "pb_bar_expand_bwd": (c_int, [_P, c_int64, _P, c_int64, c_int32, _P, _P]),
     "pb_ce_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "pb_ce_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
 }
@@ -115,6 +119,7 @@ LAUNCHES = {
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,
+    "pb_bar_pool_fwd": 1, "pb_bar_pool_bwd": 1, "pb_bar_expand_fwd": 1, "pb_bar_expand_bwd": 1,
 }
 launch_counter = {"n": 0}
 

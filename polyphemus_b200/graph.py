@@ -246,6 +246,7 @@ def graph_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = N
         raise ValueError("expected s_tensor of shape [n_bars, 4, 32]")
     g = graphs_from_tensor(s_tensor.unsqueeze(0), device=device)
     g.batch = g.bars
+    g.bar_ptr = None        # `batch` no longer indexes sequences: the per-bar segment operators do not apply
     return g
 
 

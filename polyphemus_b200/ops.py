@@ -393,6 +393,78 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
 
 
+class BarPoolFn(torch.autograd.Function):
+    """out[b] = sum over the bar's nodes of softmax(gate)_v * h[v] (pb_bar_pool_fwd / pb_bar_pool_bwd)."""
+
+    @staticmethod
+    def forward(ctx, h, gate, bar_ptr):
+        n, d = h.shape
+        n_bars = bar_ptr.numel() - 1
+        h, gate = h.float().contiguous(), gate.float().contiguous().view(-1)
+        alpha = torch.empty(n, dtype=torch.float32, device=h.device)
+        out = torch.empty((n_bars, d), dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _call("pb_bar_pool_fwd", h.data_ptr(), d, gate.data_ptr(), bar_ptr.data_ptr(), n_bars, d, alpha.data_ptr(),
+                  out.data_ptr(), _ffi.stream())
+        ctx.save_for_backward(h, alpha, bar_ptr)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        h, alpha, bar_ptr = ctx.saved_tensors
+        n, d = h.shape
+        n_bars = bar_ptr.numel() - 1
+        g_out = g_out.float().contiguous()
+        g_h = torch.empty_like(h)
+        g_gate = torch.empty(n, dtype=torch.float32, device=h.device)
+        with torch.cuda.device(h.device):
+            _call("pb_bar_pool_bwd", h.data_ptr(), d, alpha.data_ptr(), bar_ptr.data_ptr(), n_bars, d, g_out.data_ptr(),
+                  g_h.data_ptr(), d, g_gate.data_ptr(), _ffi.stream())
+        return g_h, g_gate, None
+
+
+class BarExpandFn(torch.autograd.Function):
+    """x[v] = z[bar(v)] with the deterministic segment-sum gradient (pb_bar_expand_fwd / pb_bar_expand_bwd)."""
+
+    @staticmethod
+    def forward(ctx, z, bar_ptr, n_nodes: int):
+        n_bars, d = z.shape
+        z = z.float().contiguous()
+        x = torch.empty((n_nodes, d), dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            _call("pb_bar_expand_fwd", z.data_ptr(), bar_ptr.data_ptr(), n_bars, d, x.data_ptr(), d, _ffi.stream())
+        ctx.save_for_backward(bar_ptr)
+        ctx.shape = (n_bars, d)
+        return x
+
+    @staticmethod
+    def backward(ctx, g_x):
+        (bar_ptr,) = ctx.saved_tensors
+        n_bars, d = ctx.shape
+        g_x = g_x.float().contiguous()
+        g_z = torch.empty((n_bars, d), dtype=torch.float32, device=g_x.device)
+        with torch.cuda.device(g_x.device):
+            _call("pb_bar_expand_bwd", g_x.data_ptr(), d, bar_ptr.data_ptr(), n_bars, d, g_z.data_ptr(), _ffi.stream())
+        return g_z, None, None
+
+
+def _check_bar_ptr(bar_ptr: torch.Tensor, n_bars: int) -> None:
+    if not (bar_ptr.is_cuda and bar_ptr.dtype == torch.int32 and bar_ptr.is_contiguous() and bar_ptr.numel() == n_bars + 1):
+        raise ValueError("bar_ptr must be a contiguous CUDA int32 tensor of n_bars + 1 node offsets")
+
+
+def bar_pool(h: torch.Tensor, gate: torch.Tensor, bar_ptr: torch.Tensor) -> torch.Tensor:
+    """Attention pooling of node rows h [N, d] per bar with scores gate [N]: f32 [n_bars, d]."""
+    _check_bar_ptr(bar_ptr, bar_ptr.numel() - 1)
+    return BarPoolFn.apply(h, gate.reshape(-1), bar_ptr)
+
+
+def bar_expand(z: torch.Tensor, bar_ptr: torch.Tensor, n_nodes: int) -> torch.Tensor:
+    """Rows z [n_bars, d] repeated over the nodes of their bar: f32 [n_nodes, d]."""
+    _check_bar_ptr(bar_ptr, z.size(0))
+    return BarExpandFn.apply(z, bar_ptr, n_nodes)
+
+
 class ChordEmbedFn(torch.autograd.Function):
     """chord[v] = relu(bias + sum of the node's 30 folded-table rows): pb_chord_embed_fwd; the table gradient is
     onehot^T @ (g * relu') on the split-K weight-gradient GEMM (pb_chord_embed_bwd_prep builds both operands)."""

@@ -116,8 +116,10 @@ class GlobalAttention(nn.Module):
             bn.num_batches_tracked.add_(1)
         return (g - mean) * torch.rsqrt(var + bn.eps) * bn.weight + bn.bias
 
-    def forward(self, x, batch, size: int):
+    def forward(self, x, batch, size: int, bar_ptr: Optional[torch.Tensor] = None):
         gate = self._gate(x).view(-1, 1)
+        if bar_ptr is not None and x.is_cuda and bar_ptr.numel() == size + 1:
+            return ops.bar_pool(x, gate, bar_ptr)      # segments are contiguous: fused, deterministic
         top = torch.full((size, 1), float("-inf"), dtype=gate.dtype, device=gate.device)
         top = top.scatter_reduce(0, batch.view(-1, 1), gate.detach(), reduce="amax", include_self=True)
         e = torch.exp(gate - top.index_select(0, batch))
@@ -268,7 +270,8 @@ class ContentEncoder(nn.Module):
         h = self.graph_encoder(graph)
         n_seg = _n_segments(graph, self.n_bars)
         with torch.autocast(device_type=h.device.type, enabled=False):
-            pooled = self.graph_attention(h.float(), batch=graph.distinct_bars, size=n_seg)
+            pooled = self.graph_attention(h.float(), batch=graph.distinct_bars, size=n_seg,
+                                          bar_ptr=getattr(graph, "bar_ptr", None))
         return self.bars_encoder(pooled.view(-1, self.n_bars * self.d))
 
 
@@ -344,7 +347,11 @@ class ContentDecoder(nn.Module):
         d, half = self.d, self.d // 2
         z_bar = self.bars_decoder(z_c).view(-1, d)                  # one row per (sequence, bar)
         s.distinct_bars = s.bars + self.n_bars * s.batch
-        s.x = z_bar.index_select(0, s.distinct_bars).float()        # every node starts from its bar's code
+        bar_ptr = getattr(s, "bar_ptr", None)
+        if bar_ptr is not None and z_bar.is_cuda and bar_ptr.numel() == z_bar.size(0) + 1:
+            s.x = ops.bar_expand(z_bar, bar_ptr, s.num_nodes)       # every node starts from its bar's code
+        else:
+            s.x = z_bar.index_select(0, s.distinct_bars).float()
         h = self.graph_decoder(s)
         # chord_decoder emits, per token slot, a pitch half and a duration half (model.py:549-567). Applying the
         # two row-subsets of its weight separately gives the same numbers without slicing a [N, 15, d] activation

@@ -491,3 +491,55 @@ def test_chord_embed_matches_dense_formulation(cuda, precision, d):
     tol = dict(rtol=1e-4, atol=1e-5 * scale) if precision == "fp32" else dict(rtol=2e-2, atol=2e-2 * scale)
     torch.testing.assert_close(t_dev.grad.cpu().double(), tab.grad, **tol)
     torch.testing.assert_close(b_dev.grad.cpu().double(), bias64.grad, rtol=1e-4, atol=1e-4 * float(bias64.grad.abs().max()))
+
+
+def _random_bar_ptr(n_bars, gen, max_nodes=128):
+    sizes = torch.randint(1, max_nodes + 1, (n_bars,), generator=gen)
+    sizes[0], sizes[1] = 1, max_nodes                                    # smallest and largest possible bar
+    return torch.cat((torch.zeros(1, dtype=torch.long), sizes.cumsum(0))).int(), sizes
+
+
+@pytest.mark.parametrize("d", [64, 192, 512, 1024])
+def test_bar_pool_matches_global_attention(cuda, d):
+    """ops.bar_pool == PyG GlobalAttention (softmax over the bar, weighted sum), forward and both gradients (fp64)."""
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(d)
+    bar_ptr, sizes = _random_bar_ptr(37, gen)
+    n = int(bar_ptr[-1])
+    h = torch.randn(n, d, generator=gen)
+    gate = 2.0 * torch.randn(n, generator=gen)
+    g_out = torch.randn(37, d, generator=gen)
+    seg = torch.repeat_interleave(torch.arange(37), sizes)
+
+    h_dev, gate_dev = h.to(cuda).requires_grad_(True), gate.to(cuda).requires_grad_(True)
+    out = ops.bar_pool(h_dev, gate_dev.view(-1, 1), bar_ptr.to(cuda))
+    out.backward(g_out.to(cuda))
+
+    h64, gate64 = h.double().requires_grad_(True), gate.double().requires_grad_(True)
+    top = torch.full((37,), float("-inf"), dtype=torch.float64).scatter_reduce(0, seg, gate64.detach(), "amax")
+    e = torch.exp(gate64 - top[seg])
+    alpha = e / (torch.zeros(37, dtype=torch.float64).index_add_(0, seg, e)[seg] + 1e-16)
+    ref = torch.zeros(37, d, dtype=torch.float64).index_add_(0, seg, alpha.unsqueeze(1) * h64)
+    ref.backward(g_out.double())
+    torch.testing.assert_close(out.detach().cpu().double(), ref.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(h_dev.grad.cpu().double(), h64.grad, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gate_dev.grad.cpu().double(), gate64.grad, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize("d", [64, 512])
+def test_bar_expand_and_segment_sum(cuda, d):
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(d + 1)
+    bar_ptr, sizes = _random_bar_ptr(29, gen)
+    n = int(bar_ptr[-1])
+    seg = torch.repeat_interleave(torch.arange(29), sizes)
+    z = torch.randn(29, d, generator=gen)
+    g_x = torch.randn(n, d, generator=gen)
+    z_dev = z.to(cuda).requires_grad_(True)
+    x = ops.bar_expand(z_dev, bar_ptr.to(cuda), n)
+    assert torch.equal(x.detach().cpu(), z[seg])
+    x.backward(g_x.to(cuda))
+    ref = torch.zeros(29, d, dtype=torch.float64).index_add_(0, seg, g_x.double())
+    torch.testing.assert_close(z_dev.grad.cpu().double(), ref, rtol=1e-5, atol=1e-5)
