@@ -166,6 +166,10 @@ class GradAllReducer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         dev = self.params[0].device
+        self.sync = True             # False: accumulate locally only (gradient accumulation / single-rank checks)
+        self.flat = None
+        if self.world == 1:          # nothing to exchange: plain per-parameter gradients, dropped between steps
+            return
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.buckets = []            # (start, end, n_params)
@@ -187,10 +191,8 @@ class GradAllReducer:
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._handles = []
-        self.sync = True             # False: accumulate locally only (gradient accumulation / single-rank checks)
-        if self.world > 1:
-            for p in self.params:
-                p.register_post_accumulate_grad_hook(self._hook)
+        for p in self.params:
+            p.register_post_accumulate_grad_hook(self._hook)
 
     def _launch(self, b: int) -> None:
         if self._launched[b]:
@@ -208,6 +210,10 @@ class GradAllReducer:
             self._launch(b)
 
     def zero_grad(self) -> None:
+        if self.flat is None:
+            for p in self.params:
+                p.grad = None
+            return
         self.flat.zero_()
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)

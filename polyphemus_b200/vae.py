@@ -50,6 +50,26 @@ class MLP(nn.Module):
         return x
 
 
+class _BatchNorm2d(nn.BatchNorm2d):
+    """nn.BatchNorm2d (same parameters, buffers and state-dict keys). In training on CUDA the statistics are taken
+    with plain reductions: the library's NCHW kernels run one block per channel, and with the 8 / 16 channels of the
+    structure CNNs that is 8 / 16 blocks on 148 SMs (~0.5 ms each way on a [4096, 8, 4, 32] batch)."""
+
+    def forward(self, x):
+        if not (self.training and x.is_cuda and self.track_running_stats and self.momentum is not None):
+            return super().forward(x)
+        xf = x.float()
+        var, mean = torch.var_mean(xf, dim=(0, 2, 3), unbiased=False)
+        n = x.numel() // x.size(1)
+        with torch.no_grad():
+            self.running_mean.lerp_(mean, self.momentum)
+            self.running_var.lerp_(var * (n / max(n - 1, 1)), self.momentum)
+            self.num_batches_tracked.add_(1)
+        scale = self.weight.float() * torch.rsqrt(var + self.eps)
+        shift = self.bias.float() - mean * scale
+        return (xf * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)).to(x.dtype)
+
+
 class CNNEncoder(nn.Module):
     """[*, 4, 32] structure bar -> vector (model.py:211-256); Sequential indices match the reference keys."""
 
@@ -57,10 +77,10 @@ class CNNEncoder(nn.Module):
         super().__init__()
         conv = [nn.Conv2d(1, 8, 3, padding=1)]
         if batch_norm:
-            conv.append(nn.BatchNorm2d(8))
+            conv.append(_BatchNorm2d(8))
         conv += [nn.ReLU(True), nn.MaxPool2d((1, 4), stride=(1, 4)), nn.Conv2d(8, 16, 3, padding=1)]
         if batch_norm:
-            conv.append(nn.BatchNorm2d(16))
+            conv.append(_BatchNorm2d(16))
         conv.append(nn.ReLU(True))
         self.conv = nn.Sequential(*conv)
         self.flatten = nn.Flatten(start_dim=1)
@@ -81,7 +101,7 @@ class CNNDecoder(nn.Module):
         self.unflatten = nn.Unflatten(dim=1, unflattened_size=(16, 4, 8))
         conv = [nn.Upsample(scale_factor=(1, 4), mode="nearest"), nn.Conv2d(16, 8, 3, padding=1)]
         if batch_norm:
-            conv.append(nn.BatchNorm2d(8))
+            conv.append(_BatchNorm2d(8))
         conv += [nn.ReLU(True), nn.Conv2d(8, 1, 3, padding=1)]
         self.conv = nn.Sequential(*conv)
 
