@@ -269,6 +269,16 @@ int pb_ce_fwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32
 int pb_ce_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t classes, const int32_t* target,
               int32_t ignore_index, const float* lse, const float* row_grad, void* grad, int64_t ldg,
               pb_stream_t stream);
+/* The same for n_segments heads that are consecutive column blocks (widths[s] columns each) of one logits matrix,
+ * one pass over each row: targets[s] / ignore_index[s] per head (host arrays of n_segments entries; targets[s] are
+ * device pointers), nll / lse / row_grad are [n_segments, rows]. The backward writes every column of the row. */
+#define PB_CE_MAX_SEGMENTS 4
+int pb_ce_rows_fwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,
+                   const int32_t* widths, const int32_t* const* targets, const int32_t* ignore_index, float* nll,
+                   float* lse, pb_stream_t stream);
+int pb_ce_rows_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,
+                   const int32_t* widths, const int32_t* const* targets, const int32_t* ignore_index, const float* lse,
+                   const float* row_grad, void* grad, int64_t ldg, pb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Chord embedding — replaces ContentEncoder's token embedding + BatchNorm + chord_encoder Linear + ReLU

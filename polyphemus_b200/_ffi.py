@@ -87,6 +87,8 @@ SIGNATURES = {
     "pb_bar_expand_bwd": (c_int, [_P, c_int64, _P, c_int64, c_int32, _P, _P]),
     "pb_ce_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "pb_ce_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
+    "pb_ce_rows_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
+    "pb_ce_rows_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64, _P]),
 }
 
 _lib = None
@@ -118,7 +120,7 @@ LAUNCHES = {
     "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
-    "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,
+    "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_ce_rows_fwd": 1, "pb_ce_rows_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,
     "pb_bar_pool_fwd": 1, "pb_bar_pool_bwd": 1, "pb_bar_expand_fwd": 1, "pb_bar_expand_bwd": 1,
 }
 launch_counter = {"n": 0}

@@ -144,6 +144,164 @@ ce_bwd_kernel(const void* __restrict__ logits, long ld, long rows, int classes, 
   }
 }
 
+// ---- several heads in the column blocks of one matrix: one warp per row, the whole row in one pass --------------
+struct CeSegments {
+  int n;
+  int col0[PB_CE_MAX_SEGMENTS + 1];            // block s = columns [col0[s], col0[s+1])
+  int ignore[PB_CE_MAX_SEGMENTS];
+  const int* target[PB_CE_MAX_SEGMENTS];
+};
+
+template <bool BF16, int CHUNKS, int RPW, bool BACKWARD>
+__global__ void __launch_bounds__(kCeThreads)
+ce_rows_kernel(const void* __restrict__ logits, long ld, long rows, CeSegments seg, float* __restrict__ nll,
+               float* __restrict__ lse, const float* __restrict__ row_grad, void* __restrict__ grad, long ldg) {
+  constexpr int V = BF16 ? 8 : 4;
+  const int lane = threadIdx.x & 31;
+  const long r0 = ((static_cast<long>(blockIdx.x) * kCeThreads + threadIdx.x) >> 5) * RPW;
+  const int cols = seg.col0[seg.n];
+  int my_seg[CHUNKS];                         // column block of each of this lane's chunks (-1: past the end)
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c) {
+    const int col = (c * 32 + lane) * V;
+    my_seg[c] = -1;
+    for (int s = 0; s < seg.n; ++s)
+      if (col >= seg.col0[s] && col < seg.col0[s + 1]) my_seg[c] = s;
+  }
+  float v[RPW][CHUNKS][V];
+  int tgt[RPW][PB_CE_MAX_SEGMENTS];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s)
+      tgt[i][s] = (s < seg.n && r0 + i < rows) ? __ldg(seg.target[s] + r0 + i) : (s < seg.n ? seg.ignore[s] : 0);
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      bool live = false;
+#pragma unroll
+      for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s) live |= (my_seg[c] == s) && s < seg.n && tgt[i][s] != seg.ignore[s];
+      const int col = (c * 32 + lane) * V;
+      if (live) {
+        if constexpr (BF16) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(logits) + (r0 + i) * ld + col));
+          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[i][c][2 * j] = __uint_as_float(w[j] << 16);
+            v[i][c][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+          }
+        } else {
+          const float4 raw = ldg4(static_cast<const float*>(logits) + (r0 + i) * ld + col);
+          v[i][c][0] = raw.x, v[i][c][1] = raw.y, v[i][c][2] = raw.z, v[i][c][3] = raw.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[i][c][j] = -INFINITY;
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const long r = r0 + i;
+    if (r >= rows) break;
+    float l_of[PB_CE_MAX_SEGMENTS], g_of[PB_CE_MAX_SEGMENTS];
+#pragma unroll
+    for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s) {
+      l_of[s] = 0.f, g_of[s] = 0.f;
+      if (s >= seg.n) continue;
+      const bool live = tgt[i][s] != seg.ignore[s];            // warp-uniform
+      if constexpr (BACKWARD) {
+        if (live) {
+          l_of[s] = __ldg(lse + static_cast<long>(s) * rows + r);
+          g_of[s] = __ldg(row_grad + static_cast<long>(s) * rows + r);
+        }
+      } else {
+        if (!live) {
+          if (lane == 0) nll[static_cast<long>(s) * rows + r] = 0.f, lse[static_cast<long>(s) * rows + r] = 0.f;
+          continue;
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+          if (my_seg[c] == s)
+#pragma unroll
+            for (int j = 0; j < V; ++j) m = fmaxf(m, v[i][c][j]);
+        m = warp_max(m);
+        float sum = 0.f, xt = 0.f;
+        const int tcol = seg.col0[s] + tgt[i][s];
+#pragma unroll
+        for (int c = 0; c < CHUNKS; ++c)
+          if (my_seg[c] == s)
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+              sum += expf(v[i][c][j] - m);
+              if ((c * 32 + lane) * V + j == tcol) xt = v[i][c][j];
+            }
+        sum = warp_sum(sum);
+        xt = warp_sum(xt);
+        if (lane == 0) {
+          const float l = m + logf(sum);
+          lse[static_cast<long>(s) * rows + r] = l;
+          nll[static_cast<long>(s) * rows + r] = l - xt;
+        }
+      }
+    }
+    if constexpr (BACKWARD) {
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int col = (c * 32 + lane) * V;
+        if (col >= cols) continue;
+        float l = 0.f, g = 0.f;
+        int tcol = -1;
+        bool live = false;
+#pragma unroll
+        for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s)
+          if (my_seg[c] == s && s < seg.n && tgt[i][s] != seg.ignore[s])
+            live = true, l = l_of[s], g = g_of[s], tcol = seg.col0[s] + tgt[i][s];
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = live ? (expf(v[i][c][j] - l) - (col + j == tcol ? 1.f : 0.f)) * g : 0.f;
+        if constexpr (BF16) {
+          uint4 pk;
+          uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 b = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+            w[j] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(grad) + r * ldg + col) = pk;
+        } else {
+          *reinterpret_cast<float4*>(static_cast<float*>(grad) + r * ldg + col) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+}
+
+int ce_rows_check(const char* who, const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,
+                  const int32_t* widths, const int32_t* const* targets, CeSegments* seg, int* chunks) {
+  PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "%s: dtype %d", who, dtype);
+  PB_REQUIRE(n_segments >= 1 && n_segments <= PB_CE_MAX_SEGMENTS && widths && targets, "%s: 1..%d segments", who,
+             PB_CE_MAX_SEGMENTS);
+  const int v = dtype == PB_BF16 ? 8 : 4;
+  seg->n = n_segments;
+  seg->col0[0] = 0;
+  for (int s = 0; s < n_segments; ++s) {
+    PB_REQUIRE(widths[s] > 0 && widths[s] % v == 0 && targets[s], "%s: segment %d width %d must be a multiple of %d", who, s,
+               widths[s], v);
+    seg->col0[s + 1] = seg->col0[s] + widths[s];
+    seg->target[s] = targets[s];
+  }
+  const int cols = seg->col0[n_segments];
+  PB_REQUIRE(rows >= 0 && ld >= cols && ld % v == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0,
+             "%s: row stride %lld / alignment", who, static_cast<long long>(ld));
+  const int need = (cols + 32 * v - 1) / (32 * v);
+  PB_REQUIRE(need <= 4, "%s: at most %d columns", who, 4 * 32 * v);
+  *chunks = need <= 1 ? 1 : need <= 2 ? 2 : 4;
+  return PB_OK;
+}
+
 int ce_check(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t classes, int* chunks) {
   PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "pb_ce: dtype %d", dtype);
   const int v = dtype == PB_BF16 ? 8 : 4;
@@ -195,6 +353,50 @@ extern "C" int pb_ce_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t 
              "pb_ce_bwd: grad stride %lld / alignment", static_cast<long long>(ldg));
   if (rows == 0) return PB_OK;
   PB_CE_DISPATCH(ce_bwd_kernel, logits, ld, rows, classes, target, ignore_index, lse, row_grad, grad, ldg);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+#define PB_CE_ROWS_DISPATCH(BWD, ...)                                                                          \
+  do {                                                                                                         \
+    const unsigned grid = static_cast<unsigned>(((rows + 1) / 2 + 7) / 8);                                     \
+    if (dtype == PB_BF16) {                                                                                    \
+      if (chunks == 1) ce_rows_kernel<true, 1, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else if (chunks == 2) ce_rows_kernel<true, 2, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else ce_rows_kernel<true, 4, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__);           \
+    } else {                                                                                                   \
+      if (chunks == 1) ce_rows_kernel<false, 1, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else if (chunks == 2) ce_rows_kernel<false, 2, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
+      else ce_rows_kernel<false, 4, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__);          \
+    }                                                                                                          \
+  } while (0)
+
+extern "C" int pb_ce_rows_fwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,
+                              const int32_t* widths, const int32_t* const* targets, const int32_t* ignore_index,
+                              float* nll, float* lse, pb_stream_t stream) {
+  CeSegments seg{};
+  int chunks = 0;
+  if (int rc = ce_rows_check("pb_ce_rows_fwd", logits, ld, dtype, rows, n_segments, widths, targets, &seg, &chunks)) return rc;
+  PB_REQUIRE(ignore_index && nll && lse, "pb_ce_rows_fwd: null pointer");
+  for (int s = 0; s < n_segments; ++s) seg.ignore[s] = ignore_index[s];
+  if (rows == 0) return PB_OK;
+  PB_CE_ROWS_DISPATCH(false, logits, ld, rows, seg, nll, lse, nullptr, nullptr, 0);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_ce_rows_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,
+                              const int32_t* widths, const int32_t* const* targets, const int32_t* ignore_index,
+                              const float* lse, const float* row_grad, void* grad, int64_t ldg, pb_stream_t stream) {
+  CeSegments seg{};
+  int chunks = 0;
+  if (int rc = ce_rows_check("pb_ce_rows_bwd", logits, ld, dtype, rows, n_segments, widths, targets, &seg, &chunks)) return rc;
+  PB_REQUIRE(ignore_index && lse && row_grad && grad, "pb_ce_rows_bwd: null pointer");
+  PB_REQUIRE(ldg % (dtype == PB_BF16 ? 8 : 4) == 0 && ldg >= seg.col0[n_segments] && reinterpret_cast<uintptr_t>(grad) % 16 == 0,
+             "pb_ce_rows_bwd: grad stride %lld / alignment", static_cast<long long>(ldg));
+  for (int s = 0; s < n_segments; ++s) seg.ignore[s] = ignore_index[s];
+  if (rows == 0) return PB_OK;
+  PB_CE_ROWS_DISPATCH(true, logits, ld, rows, seg, nullptr, const_cast<float*>(lse), row_grad, grad, ldg);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

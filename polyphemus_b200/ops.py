@@ -554,42 +554,49 @@ class TokenNllFn(torch.autograd.Function):
         return grad, None, None
 
 
+def _segment_args(specs, targets):
+    """Host-side argument arrays of pb_ce_rows_*: widths, device target pointers, ignored ids."""
+    import ctypes
+
+    n = len(specs)
+    widths = (ctypes.c_int32 * n)(*[w for _, w, _ in specs])
+    ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in targets])
+    ignore = (ctypes.c_int32 * n)(*[i for _, _, i in specs])
+    return widths, ptrs, ignore
+
+
 class TokenNllSegmentsFn(torch.autograd.Function):
     """TokenNllFn for several heads that share one logits matrix: head i owns the column block
-    [col0_i, col0_i + width_i) of ``logits`` [rows, cols] and has its own targets / ignored id. The blocks tile the
-    columns, so the backward fills ONE gradient matrix in place (no per-head slices to zero-fill and add up)."""
+    [col0_i, col0_i + width_i) of ``logits`` [rows, cols] and has its own targets / ignored id. One pass over each row
+    per direction (pb_ce_rows_fwd / pb_ce_rows_bwd); the blocks tile the columns, so the backward fills ONE gradient
+    matrix (no per-head slices to zero-fill and add up)."""
 
     @staticmethod
     def forward(ctx, logits, specs, *targets):
-        rows = logits.size(0)
+        rows, n = logits.size(0), len(specs)
         dtype = _ffi.PB_BF16 if logits.dtype == torch.bfloat16 else _ffi.PB_F32
-        es = logits.element_size()
-        outs, lses = [], []
+        nll = torch.empty((n, rows), dtype=torch.float32, device=logits.device)
+        lse = torch.empty((n, rows), dtype=torch.float32, device=logits.device)
+        widths, ptrs, ignore = _segment_args(specs, targets)
         with torch.cuda.device(logits.device):
-            for (col0, width, ignore), target in zip(specs, targets):
-                nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
-                lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
-                _call("pb_ce_fwd", logits.data_ptr() + col0 * es, logits.stride(0), dtype, rows, width, target.data_ptr(),
-                      int(ignore), nll.data_ptr(), lse.data_ptr(), _ffi.stream())
-                outs.append(nll)
-                lses.append(lse)
-        ctx.save_for_backward(logits, *targets, *lses)
+            _call("pb_ce_rows_fwd", logits.data_ptr(), logits.stride(0), dtype, rows, n, widths, ptrs, ignore,
+                  nll.data_ptr(), lse.data_ptr(), _ffi.stream())
+        ctx.save_for_backward(logits, lse, *targets)
         ctx.specs, ctx.dtype = specs, dtype
-        return tuple(outs)
+        return tuple(nll.unbind(0))
 
     @staticmethod
     def backward(ctx, *gs):
         n = len(ctx.specs)
-        logits, targets, lses = ctx.saved_tensors[0], ctx.saved_tensors[1:1 + n], ctx.saved_tensors[1 + n:]
+        logits, lse, targets = ctx.saved_tensors[0], ctx.saved_tensors[1], ctx.saved_tensors[2:]
         rows, cols = logits.shape
-        es = logits.element_size()
+        row_grad = torch.stack([torch.zeros(rows, dtype=torch.float32, device=logits.device) if g is None else g.float()
+                                for g in gs]).contiguous()
         grad = torch.empty((rows, cols), dtype=logits.dtype, device=logits.device)
+        widths, ptrs, ignore = _segment_args(ctx.specs, targets)
         with torch.cuda.device(logits.device):
-            for (col0, width, ignore), target, lse, g in zip(ctx.specs, targets, lses, gs):
-                g = torch.zeros(rows, dtype=torch.float32, device=logits.device) if g is None else g.float().contiguous()
-                _call("pb_ce_bwd", logits.data_ptr() + col0 * es, logits.stride(0), ctx.dtype, rows, width,
-                      target.data_ptr(), int(ignore), lse.data_ptr(), g.data_ptr(), grad.data_ptr() + col0 * es, cols,
-                      _ffi.stream())
+            _call("pb_ce_rows_bwd", logits.data_ptr(), logits.stride(0), ctx.dtype, rows, n, widths, ptrs, ignore,
+                  lse.data_ptr(), row_grad.data_ptr(), grad.data_ptr(), cols, _ffi.stream())
         return (grad, None) + (None,) * n
 
 
