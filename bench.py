@@ -140,6 +140,17 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ roofline
+def ncu_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel family, from the committed `ncu --set full`
+    captures (profiles/traffic.json, written by tools/summarize_profiles.py) — measured once under the profiler, not
+    during this run."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as fh:
+        return json.load(fh)
+
+
 def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: str, pk: dict, p_drop: float,
                  slots: int = 6, n_rows: int = 0):
     """Per-kernel-family algorithmic bytes / flops per launch and achieved rates.
@@ -313,8 +324,11 @@ def main():
         hbm_ms = sum(r["ms_per_step"] for r in hbm_rows)
         roofline = None
         if top:
+            traffic = ncu_traffic().get(top["kernel"], {})
             roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                        "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": pk["source"],
+                        "unit": top["unit"], "frac": top["frac"], "traffic": traffic.get("bytes_per_launch"),
+                        "traffic_source": traffic.get("source"), "peak_source": pk["source"],
+                        "algorithmic_per_launch": top["algorithmic_per_launch"],
                         "share_of_step": top["ms_per_step"] / (total_ms / args.steps)}
         cpu = None
         if not args.no_cpu_baseline:

@@ -40,6 +40,14 @@ __device__ __forceinline__ void ce_load_row(const void* logits, long ld, long r,
   }
 }
 
+// exp of a softmax term (argument <= 0). bf16 logits: ex2.approx on x * log2(e), relative error ~2^-21 — far below the
+// rounding of the logits themselves and of the bf16 gradient, 2 instructions instead of ~12. fp32 logits: expf.
+template <bool BF16>
+__device__ __forceinline__ float ce_exp(float x) {
+  if constexpr (BF16) return __expf(x);
+  else return expf(x);
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -82,7 +90,7 @@ ce_fwd_kernel(const void* __restrict__ logits, long ld, long rows, int classes, 
     for (int c = 0; c < CHUNKS; ++c)
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        s += expf(v[i][c][j] - m);
+        s += ce_exp<BF16>(v[i][c][j] - m);
         if ((c * 32 + lane) * V + j == tgt[i]) xt = v[i][c][j];
       }
     s = warp_sum(s);
@@ -125,9 +133,13 @@ ce_bwd_kernel(const void* __restrict__ logits, long ld, long rows, int classes, 
       const int col = (c * 32 + lane) * V;
       if (col >= classes) continue;
       float o[V];
+      if (live) {                                                // warp-uniform
 #pragma unroll
-      for (int j = 0; j < V; ++j)
-        o[j] = live ? (expf(v[i][c][j] - l[i]) - (col + j == tgt[i] ? 1.f : 0.f)) * rg[i] : 0.f;
+        for (int j = 0; j < V; ++j) o[j] = (ce_exp<BF16>(v[i][c][j] - l[i]) - (col + j == tgt[i] ? 1.f : 0.f)) * rg[i];
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = 0.f;
+      }
       if constexpr (BF16) {
         uint4 pk;
         uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
@@ -152,130 +164,147 @@ struct CeSegments {
   const int* target[PB_CE_MAX_SEGMENTS];
 };
 
-template <bool BF16, int CHUNKS, int RPW, bool BACKWARD>
+// One warp per RPW = 4 consecutive rows. The (row, segment) targets / log-sum-exps / row gradients are fetched
+// lane-parallel (one coalesced load each, then shuffles), every live (row, segment) block is loaded as raw 16-byte
+// chunks before the first use (CPS chunks per lane and segment: width <= 32 * V * CPS), and ignored blocks are never
+// read. Segment loops are unrolled over the template segment count S, so the by-value struct stays in the constant
+// bank. The backward writes whole rows (zeros for ignored blocks).
+template <bool BF16> struct CeRaw { using type = float4; };
+template <> struct CeRaw<true> { using type = uint4; };
+
+template <bool BF16>
+__device__ __forceinline__ void ce_unpack(const typename CeRaw<BF16>::type& raw, float (&o)[BF16 ? 8 : 4]) {
+  if constexpr (BF16) {
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[2 * j] = __uint_as_float(w[j] << 16);
+      o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+    }
+  } else {
+    o[0] = raw.x, o[1] = raw.y, o[2] = raw.z, o[3] = raw.w;
+  }
+}
+
+template <bool BF16, int CPS, int RPW, int S, bool BACKWARD>
 __global__ void __launch_bounds__(kCeThreads)
 ce_rows_kernel(const void* __restrict__ logits, long ld, long rows, CeSegments seg, float* __restrict__ nll,
                float* __restrict__ lse, const float* __restrict__ row_grad, void* __restrict__ grad, long ldg) {
   constexpr int V = BF16 ? 8 : 4;
+  constexpr uint32_t kFull = 0xffffffffu;
+  static_assert(RPW * S <= 32, "one lane per (row, segment)");
+  using Raw = typename CeRaw<BF16>::type;
   const int lane = threadIdx.x & 31;
   const long r0 = ((static_cast<long>(blockIdx.x) * kCeThreads + threadIdx.x) >> 5) * RPW;
-  const int cols = seg.col0[seg.n];
-  int my_seg[CHUNKS];                         // column block of each of this lane's chunks (-1: past the end)
+  // lane = s * RPW + i holds the scalars of (row i, segment s)
+  const int my_s = lane / RPW, my_i = lane % RPW;
+  int my_tgt = 0;
+  bool my_live = false;
+  float my_l = 0.f, my_g = 0.f;
 #pragma unroll
-  for (int c = 0; c < CHUNKS; ++c) {
-    const int col = (c * 32 + lane) * V;
-    my_seg[c] = -1;
-    for (int s = 0; s < seg.n; ++s)
-      if (col >= seg.col0[s] && col < seg.col0[s + 1]) my_seg[c] = s;
-  }
-  float v[RPW][CHUNKS][V];
-  int tgt[RPW][PB_CE_MAX_SEGMENTS];
-#pragma unroll
-  for (int i = 0; i < RPW; ++i)
-#pragma unroll
-    for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s)
-      tgt[i][s] = (s < seg.n && r0 + i < rows) ? __ldg(seg.target[s] + r0 + i) : (s < seg.n ? seg.ignore[s] : 0);
-#pragma unroll
-  for (int i = 0; i < RPW; ++i)
-#pragma unroll
-    for (int c = 0; c < CHUNKS; ++c) {
-      bool live = false;
-#pragma unroll
-      for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s) live |= (my_seg[c] == s) && s < seg.n && tgt[i][s] != seg.ignore[s];
-      const int col = (c * 32 + lane) * V;
-      if (live) {
-        if constexpr (BF16) {
-          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(logits) + (r0 + i) * ld + col));
-          const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[i][c][2 * j] = __uint_as_float(w[j] << 16);
-            v[i][c][2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
-          }
-        } else {
-          const float4 raw = ldg4(static_cast<const float*>(logits) + (r0 + i) * ld + col);
-          v[i][c][0] = raw.x, v[i][c][1] = raw.y, v[i][c][2] = raw.z, v[i][c][3] = raw.w;
+  for (int s = 0; s < S; ++s)
+    if (my_s == s && r0 + my_i < rows) {
+      my_tgt = __ldg(seg.target[s] + r0 + my_i);
+      my_live = my_tgt != seg.ignore[s];
+      if constexpr (BACKWARD)
+        if (my_live) {
+          my_l = __ldg(lse + static_cast<long>(s) * rows + r0 + my_i);
+          my_g = __ldg(row_grad + static_cast<long>(s) * rows + r0 + my_i);
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[i][c][j] = -INFINITY;
-      }
     }
+  const uint32_t live_mask = __ballot_sync(kFull, my_live);
+  Raw raw[RPW][S][CPS];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i)
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+      for (int c = 0; c < CPS; ++c) {
+        const int col = seg.col0[s] + (c * 32 + lane) * V;
+        if (((live_mask >> (s * RPW + i)) & 1u) && col < seg.col0[s + 1]) {
+          if constexpr (BF16)
+            raw[i][s][c] = __ldg(reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(logits) + (r0 + i) * ld + col));
+          else
+            raw[i][s][c] = ldg4(static_cast<const float*>(logits) + (r0 + i) * ld + col);
+        } else {
+          if constexpr (BF16) raw[i][s][c] = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf
+          else raw[i][s][c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+      }
+  float my_nll = 0.f, my_lse = 0.f;       // forward results of this lane's (row, segment)
 #pragma unroll
   for (int i = 0; i < RPW; ++i) {
     const long r = r0 + i;
-    if (r >= rows) break;
-    float l_of[PB_CE_MAX_SEGMENTS], g_of[PB_CE_MAX_SEGMENTS];
 #pragma unroll
-    for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s) {
-      l_of[s] = 0.f, g_of[s] = 0.f;
-      if (s >= seg.n) continue;
-      const bool live = tgt[i][s] != seg.ignore[s];            // warp-uniform
-      if constexpr (BACKWARD) {
-        if (live) {
-          l_of[s] = __ldg(lse + static_cast<long>(s) * rows + r);
-          g_of[s] = __ldg(row_grad + static_cast<long>(s) * rows + r);
-        }
-      } else {
-        if (!live) {
-          if (lane == 0) nll[static_cast<long>(s) * rows + r] = 0.f, lse[static_cast<long>(s) * rows + r] = 0.f;
-          continue;
-        }
+    for (int s = 0; s < S; ++s) {
+      const int owner = s * RPW + i;
+      const bool live = (live_mask >> owner) & 1u;               // warp-uniform
+      const int tgt = __shfl_sync(kFull, my_tgt, owner);
+      if constexpr (!BACKWARD) {
+        if (!live) continue;
+        float v[CPS][V];
         float m = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
-          if (my_seg[c] == s)
+        for (int c = 0; c < CPS; ++c) {
+          ce_unpack<BF16>(raw[i][s][c], v[c]);
 #pragma unroll
-            for (int j = 0; j < V; ++j) m = fmaxf(m, v[i][c][j]);
+          for (int j = 0; j < V; ++j) m = fmaxf(m, v[c][j]);
+        }
         m = warp_max(m);
         float sum = 0.f, xt = 0.f;
-        const int tcol = seg.col0[s] + tgt[i][s];
 #pragma unroll
-        for (int c = 0; c < CHUNKS; ++c)
-          if (my_seg[c] == s)
+        for (int c = 0; c < CPS; ++c)
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-              sum += expf(v[i][c][j] - m);
-              if ((c * 32 + lane) * V + j == tcol) xt = v[i][c][j];
-            }
+          for (int j = 0; j < V; ++j) {
+            sum += ce_exp<BF16>(v[c][j] - m);
+            if ((c * 32 + lane) * V + j == tgt) xt = v[c][j];
+          }
         sum = warp_sum(sum);
         xt = warp_sum(xt);
-        if (lane == 0) {
-          const float l = m + logf(sum);
-          lse[static_cast<long>(s) * rows + r] = l;
-          nll[static_cast<long>(s) * rows + r] = l - xt;
+        if (lane == owner) {
+          my_lse = m + logf(sum);
+          my_nll = my_lse - xt;
         }
-      }
-    }
-    if constexpr (BACKWARD) {
+      } else {
+        if (r >= rows) continue;
+        const float l = __shfl_sync(kFull, my_l, owner), g = __shfl_sync(kFull, my_g, owner);
 #pragma unroll
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int col = (c * 32 + lane) * V;
-        if (col >= cols) continue;
-        float l = 0.f, g = 0.f;
-        int tcol = -1;
-        bool live = false;
+        for (int c = 0; c < CPS; ++c) {
+          const int rel = (c * 32 + lane) * V;
+          const int col = seg.col0[s] + rel;
+          if (col >= seg.col0[s + 1]) continue;
+          float v[V], o[V];
+          if (live) {                                            // warp-uniform branch: ignored blocks cost a store only
+            ce_unpack<BF16>(raw[i][s][c], v);
 #pragma unroll
-        for (int s = 0; s < PB_CE_MAX_SEGMENTS; ++s)
-          if (my_seg[c] == s && s < seg.n && tgt[i][s] != seg.ignore[s])
-            live = true, l = l_of[s], g = g_of[s], tcol = seg.col0[s] + tgt[i][s];
-        float o[V];
+            for (int j = 0; j < V; ++j) o[j] = (ce_exp<BF16>(v[j] - l) - (rel + j == tgt ? 1.f : 0.f)) * g;
+          } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) o[j] = live ? (expf(v[i][c][j] - l) - (col + j == tcol ? 1.f : 0.f)) * g : 0.f;
-        if constexpr (BF16) {
-          uint4 pk;
-          uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const __nv_bfloat162 b = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-            w[j] = *reinterpret_cast<const uint32_t*>(&b);
+            for (int j = 0; j < V; ++j) o[j] = 0.f;
           }
-          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(grad) + r * ldg + col) = pk;
-        } else {
-          *reinterpret_cast<float4*>(static_cast<float*>(grad) + r * ldg + col) = make_float4(o[0], o[1], o[2], o[3]);
+          if constexpr (BF16) {
+            uint4 pk;
+            uint32_t* w = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const __nv_bfloat162 b = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&b);
+            }
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(grad) + r * ldg + col) = pk;
+          } else {
+            *reinterpret_cast<float4*>(static_cast<float*>(grad) + r * ldg + col) = make_float4(o[0], o[1], o[2], o[3]);
+          }
         }
       }
     }
+  }
+  if constexpr (!BACKWARD) {
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if (my_s == s && r0 + my_i < rows) {
+        nll[static_cast<long>(s) * rows + r0 + my_i] = my_nll;       // 0 for ignored rows
+        lse[static_cast<long>(s) * rows + r0 + my_i] = my_lse;
+      }
   }
 }
 
@@ -296,9 +325,11 @@ int ce_rows_check(const char* who, const void* logits, int64_t ld, int32_t dtype
   const int cols = seg->col0[n_segments];
   PB_REQUIRE(rows >= 0 && ld >= cols && ld % v == 0 && reinterpret_cast<uintptr_t>(logits) % 16 == 0,
              "%s: row stride %lld / alignment", who, static_cast<long long>(ld));
-  const int need = (cols + 32 * v - 1) / (32 * v);
-  PB_REQUIRE(need <= 4, "%s: at most %d columns", who, 4 * 32 * v);
-  *chunks = need <= 1 ? 1 : need <= 2 ? 2 : 4;
+  int widest = 0;
+  for (int s = 0; s < n_segments; ++s) widest = std::max(widest, widths[s]);
+  const int need = (widest + 32 * v - 1) / (32 * v);
+  PB_REQUIRE(need <= 2, "%s: at most %d columns per segment", who, 2 * 32 * v);
+  *chunks = need;
   return PB_OK;
 }
 
@@ -357,18 +388,25 @@ extern "C" int pb_ce_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t 
   return PB_OK;
 }
 
-#define PB_CE_ROWS_DISPATCH(BWD, ...)                                                                          \
-  do {                                                                                                         \
-    const unsigned grid = static_cast<unsigned>(((rows + 1) / 2 + 7) / 8);                                     \
-    if (dtype == PB_BF16) {                                                                                    \
-      if (chunks == 1) ce_rows_kernel<true, 1, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
-      else if (chunks == 2) ce_rows_kernel<true, 2, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
-      else ce_rows_kernel<true, 4, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__);           \
-    } else {                                                                                                   \
-      if (chunks == 1) ce_rows_kernel<false, 1, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
-      else if (chunks == 2) ce_rows_kernel<false, 2, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__); \
-      else ce_rows_kernel<false, 4, 2, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__);          \
-    }                                                                                                          \
+#define PB_CE_ROWS_LAUNCH(BF, CPS, S, BWD, ...) \
+  ce_rows_kernel<BF, CPS, 4, S, BWD><<<grid, kCeThreads, 0, as_stream(stream)>>>(__VA_ARGS__)
+#define PB_CE_ROWS_BY_SEG(BF, CPS, BWD, ...)                             \
+  do {                                                                   \
+    if (n_segments == 1) PB_CE_ROWS_LAUNCH(BF, CPS, 1, BWD, __VA_ARGS__); \
+    else if (n_segments == 2) PB_CE_ROWS_LAUNCH(BF, CPS, 2, BWD, __VA_ARGS__); \
+    else if (n_segments == 3) PB_CE_ROWS_LAUNCH(BF, CPS, 3, BWD, __VA_ARGS__); \
+    else PB_CE_ROWS_LAUNCH(BF, CPS, 4, BWD, __VA_ARGS__);                \
+  } while (0)
+#define PB_CE_ROWS_DISPATCH(BWD, ...)                                            \
+  do {                                                                           \
+    const unsigned grid = static_cast<unsigned>(((rows + 3) / 4 + 7) / 8);       \
+    if (dtype == PB_BF16) {                                                      \
+      if (chunks == 1) PB_CE_ROWS_BY_SEG(true, 1, BWD, __VA_ARGS__);             \
+      else PB_CE_ROWS_BY_SEG(true, 2, BWD, __VA_ARGS__);                         \
+    } else {                                                                     \
+      if (chunks == 1) PB_CE_ROWS_BY_SEG(false, 1, BWD, __VA_ARGS__);            \
+      else PB_CE_ROWS_BY_SEG(false, 2, BWD, __VA_ARGS__);                        \
+    }                                                                            \
   } while (0)
 
 extern "C" int pb_ce_rows_fwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, int32_t n_segments,

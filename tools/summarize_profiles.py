@@ -74,5 +74,51 @@ def rep_summaries():
         print("wrote", name)
 
 
+def traffic_json():
+    """profiles/traffic.json: measured DRAM bytes per launch of each kernel family (bench.py's roofline.traffic)."""
+    import json
+    import re
+
+    families = {   # ABI call -> (summary file, kernel-name prefixes whose launches make up one call)
+        "pb_agg_fwd": ("aggfwd", ["agg_fwd_kernel"]),
+        "pb_agg_bwd": ("aggbwd", ["agg_bwd_dx_kernel"]),
+        "pb_dist_reduce": ("distred", ["dist_reduce_kernel"]),
+        "pb_rgcn_gemm_fwd": ("gemm", ["gemm_tcgen05_kernel"]),
+        "pb_bn_relu_res_fwd": ("bn", ["bn_apply_kernel"]),
+        "pb_bn_stats": ("bn", ["bn_stats_partial_kernel", "bn_stats_finalize_kernel"]),
+    }
+    out = {}
+    for call, (stem, prefixes) in families.items():
+        path = os.path.join(dst, f"{tag}_ncu_{stem}.txt")
+        if not os.path.exists(path):
+            continue
+        per_kernel, cur = {}, None
+        for line in open(path):
+            if line.startswith("kernel:"):
+                cur = line.split("kernel:")[1].strip()
+                cur = re.sub(r"^void ", "", cur).split("<")[0].split("(")[0]
+                per_kernel.setdefault(cur, []).append(0.0)
+            elif cur and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
+                val, unit = line.split()[-2:]
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+                per_kernel[cur][-1] += float(val) * mult
+        total, found = 0.0, []
+        for pre in prefixes:
+            if pre in per_kernel:
+                total += sum(per_kernel[pre]) / len(per_kernel[pre])
+                found.append(pre)
+        if found:
+            out[call] = {"bytes_per_launch": total, "kernels": found,
+                         "source": f"profiles/{tag}_ncu_{stem}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+    if "pb_agg_bwd" in out and "pb_dist_reduce" in out:     # the deterministic path = both kernels
+        out["pb_agg_bwd"]["bytes_per_launch"] += out["pb_dist_reduce"]["bytes_per_launch"]
+        out["pb_agg_bwd"]["kernels"] += out["pb_dist_reduce"]["kernels"]
+        out["pb_agg_bwd"]["source"] += f" + profiles/{tag}_ncu_distred.txt"
+    out.pop("pb_dist_reduce", None)
+    json.dump(out, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
+    print("wrote traffic.json:", {k: round(v["bytes_per_launch"] / 1e6, 1) for k, v in out.items()}, "MB")
+
+
 launch_shares()
 rep_summaries()
+traffic_json()
