@@ -48,6 +48,12 @@ __device__ __forceinline__ float ce_exp(float x) {
   else return expf(x);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -231,17 +237,24 @@ ce_rows_kernel(const void* __restrict__ logits, long ld, long rows, CeSegments s
           else raw[i][s][c] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
       }
-  float my_nll = 0.f, my_lse = 0.f;       // forward results of this lane's (row, segment)
+  constexpr float kLog2e = 1.4426950408889634f;
+  if constexpr (!BACKWARD) {
+    // the target logit of this lane's (row, segment): one scalar load (the row is being fetched anyway)
+    float my_xt = 0.f;
 #pragma unroll
-  for (int i = 0; i < RPW; ++i) {
-    const long r = r0 + i;
+    for (int s = 0; s < S; ++s)
+      if (my_s == s && my_live) {
+        const long off = (r0 + my_i) * ld + seg.col0[s] + my_tgt;
+        if constexpr (BF16) my_xt = __bfloat162float(static_cast<const __nv_bfloat16*>(logits)[off]);
+        else my_xt = static_cast<const float*>(logits)[off];
+      }
+    float my_m = 0.f, my_sum = 1.f;
 #pragma unroll
-    for (int s = 0; s < S; ++s) {
-      const int owner = s * RPW + i;
-      const bool live = (live_mask >> owner) & 1u;               // warp-uniform
-      const int tgt = __shfl_sync(kFull, my_tgt, owner);
-      if constexpr (!BACKWARD) {
-        if (!live) continue;
+    for (int i = 0; i < RPW; ++i)
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int owner = s * RPW + i;
+        if (!((live_mask >> owner) & 1u)) continue;                // warp-uniform
         float v[CPS][V];
         float m = -INFINITY;
 #pragma unroll
@@ -251,33 +264,60 @@ ce_rows_kernel(const void* __restrict__ logits, long ld, long rows, CeSegments s
           for (int j = 0; j < V; ++j) m = fmaxf(m, v[c][j]);
         }
         m = warp_max(m);
-        float sum = 0.f, xt = 0.f;
+        float sum = 0.f;
+        if constexpr (BF16) {                                      // ex2.approx(v log2e - m log2e): 2 instructions a term
+          const float ms = m * kLog2e;
 #pragma unroll
-        for (int c = 0; c < CPS; ++c)
+          for (int c = 0; c < CPS; ++c)
 #pragma unroll
-          for (int j = 0; j < V; ++j) {
-            sum += ce_exp<BF16>(v[c][j] - m);
-            if ((c * 32 + lane) * V + j == tgt) xt = v[c][j];
-          }
-        sum = warp_sum(sum);
-        xt = warp_sum(xt);
-        if (lane == owner) {
-          my_lse = m + logf(sum);
-          my_nll = my_lse - xt;
+            for (int j = 0; j < V; ++j) sum += ex2_approx(fmaf(v[c][j], kLog2e, -ms));
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPS; ++c)
+#pragma unroll
+            for (int j = 0; j < V; ++j) sum += expf(v[c][j] - m);
         }
-      } else {
-        if (r >= rows) continue;
+        sum = warp_sum(sum);
+        if (lane == owner) my_m = m, my_sum = sum;
+      }
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+      if (my_s == s && r0 + my_i < rows) {
+        const float l = my_live ? my_m + logf(my_sum) : 0.f;       // one logf per lane, not per block
+        lse[static_cast<long>(s) * rows + r0 + my_i] = l;
+        nll[static_cast<long>(s) * rows + r0 + my_i] = my_live ? l - my_xt : 0.f;
+      }
+  } else {
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const long r = r0 + i;
+      if (r >= rows) break;                                        // warp-uniform
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        const int owner = s * RPW + i;
+        const bool live = (live_mask >> owner) & 1u;               // warp-uniform
+        const int tgt = __shfl_sync(kFull, my_tgt, owner);
         const float l = __shfl_sync(kFull, my_l, owner), g = __shfl_sync(kFull, my_g, owner);
 #pragma unroll
         for (int c = 0; c < CPS; ++c) {
           const int rel = (c * 32 + lane) * V;
           const int col = seg.col0[s] + rel;
           if (col >= seg.col0[s + 1]) continue;
-          float v[V], o[V];
-          if (live) {                                            // warp-uniform branch: ignored blocks cost a store only
+          float o[V];
+          if (live) {                                              // ignored blocks cost a store only
+            float v[V];
             ce_unpack<BF16>(raw[i][s][c], v);
+            if constexpr (BF16) {
+              const float ls = l * kLog2e;
 #pragma unroll
-            for (int j = 0; j < V; ++j) o[j] = (ce_exp<BF16>(v[j] - l) - (rel + j == tgt ? 1.f : 0.f)) * g;
+              for (int j = 0; j < V; ++j) o[j] = ex2_approx(fmaf(v[j], kLog2e, -ls)) * g;
+            } else {
+#pragma unroll
+              for (int j = 0; j < V; ++j) o[j] = expf(v[j] - l) * g;
+            }
+            const int hit = tgt - rel;                              // the one-hot term lands in at most one lane
+#pragma unroll
+            for (int j = 0; j < V; ++j) o[j] -= (hit == j) ? g : 0.f;   // select, not a branch
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j) o[j] = 0.f;
@@ -297,14 +337,6 @@ ce_rows_kernel(const void* __restrict__ logits, long ld, long rows, CeSegments s
         }
       }
     }
-  }
-  if constexpr (!BACKWARD) {
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-      if (my_s == s && r0 + my_i < rows) {
-        nll[static_cast<long>(s) * rows + r0 + my_i] = my_nll;       // 0 for ignored rows
-        lse[static_cast<long>(s) * rows + r0 + my_i] = my_lse;
-      }
   }
 }
 
