@@ -173,15 +173,14 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
         "pb_rgcn_gemm_bwd_weight": ("tensor", 2 * n_rows * k * d),
     }
     mma_passes = 1 if precision == "bf16" else 3
-    layer_calls = summary["pb_agg_fwd"]["calls"] / steps if "pb_agg_fwd" in summary else 16   # GCL layers per step
-    layer_calls_bwd = summary["pb_agg_bwd"]["calls"] / steps if "pb_agg_bwd" in summary else layer_calls
     rows = []
     for name, (bound, work) in algo.items():
         if name not in summary:
             continue
         ent = summary[name]
-        # `work` is per layer call; a family may take several launches per layer (grouped weight gradient)
-        per_layer_s = ent["ms"] / steps / (layer_calls if name in ("pb_agg_fwd",) else layer_calls_bwd if "bwd" in name else layer_calls) * 1e-3
+        # `work` is per ABI call = per layer (a call may be several launches, e.g. the grouped weight gradient; an
+        # operand recompute in backward is one more pb_agg_fwd call)
+        per_layer_s = ent["ms"] / ent["calls"] * 1e-3
         if bound == "hbm":
             achieved, peak, unit = work / per_layer_s / 1e9, pk["hbm"], "GB/s"
         else:

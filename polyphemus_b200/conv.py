@@ -155,10 +155,10 @@ class GCN(nn.Module):
         if st is not None and self.batch_norm and self.p == 0 and x.size(1) % 256 == 0 and x.is_cuda:
             # structured layout: nodes sorted by track relation, groups padded to the GEMM tile (zero rows), the
             # whole stack runs on [Np, d]; one gather in, one gather out
-            xp = torch.zeros((st.n_padded, x.size(1)), dtype=x.dtype, device=x.device).index_copy(0, st.pos, x)
+            xp = ops.ScatterRowsFn.apply(x, st.pos, st.n_padded)
             for i, layer in enumerate(self.layers):
                 xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st)
-            return xp.index_select(0, st.pos)
+            return ops.GatherRowsFn.apply(xp, st.pos)
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):
             residual = x

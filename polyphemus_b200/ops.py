@@ -393,6 +393,37 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
 
 
+class ScatterRowsFn(torch.autograd.Function):
+    """out = zeros(n_rows, d); out[pos] = x for an injective row map ``pos`` (node -> padded row of the structured
+    layout). The gradient is a plain gather — autograd's own formula for index_copy / index_select goes through
+    index_add_ (atomic adds), which an injective map does not need."""
+
+    @staticmethod
+    def forward(ctx, x, pos, n_rows: int):
+        ctx.save_for_backward(pos)
+        return torch.zeros((n_rows, x.size(1)), dtype=x.dtype, device=x.device).index_copy_(0, pos, x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        return g.index_select(0, pos), None, None
+
+
+class GatherRowsFn(torch.autograd.Function):
+    """out = xp[pos] for an injective ``pos``; the gradient scatters with index_copy_ (rows nobody read get zero)."""
+
+    @staticmethod
+    def forward(ctx, xp, pos):
+        ctx.save_for_backward(pos)
+        ctx.n_rows = xp.size(0)
+        return xp.index_select(0, pos)
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        return torch.zeros((ctx.n_rows, g.size(1)), dtype=g.dtype, device=g.device).index_copy_(0, pos, g), None
+
+
 class BarPoolFn(torch.autograd.Function):
     """out[b] = sum over the bar's nodes of softmax(gate)_v * h[v] (pb_bar_pool_fwd / pb_bar_pool_bwd)."""
 
