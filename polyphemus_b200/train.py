@@ -154,11 +154,13 @@ def device_batch(host: HostBatch, device, onehot: bool = False, onehot_dtype=tor
 class GradAllReducer:
     """Flat-buffer gradient all-reduce (sum then 1/world) overlapped with backward.
 
-    Every parameter's ``.grad`` is a view into one contiguous fp32 buffer. Parameters are bucketed in reverse
-    registration order (the order backward produces them); a post-accumulate hook counts ready parameters and
-    launches ``all_reduce`` on a bucket the moment it is complete. Parameters that never receive a gradient
-    (the 12 ``decoder.s_decoder.*`` tensors, whose loss term is constant — training.py:307) keep a zero slot,
-    identically on every rank, and their buckets are flushed by ``finish()``.
+    Parameters are bucketed in reverse registration order (the order backward produces them) over one contiguous
+    fp32 buffer. Backward leaves every gradient where autograd puts it (no per-parameter accumulation kernels); a
+    post-accumulate hook counts ready parameters, and the moment a bucket is complete its gradients are packed into
+    the buffer with ONE multi-tensor copy and ``all_reduce`` is launched on that slice. ``finish()`` flushes the
+    buckets of parameters that never receive a gradient (the 12 ``decoder.s_decoder.*`` tensors, whose loss term is
+    constant — training.py:307 — keep a zero slot, identically on every rank), waits, averages, and points every
+    ``.grad`` at its slice of the buffer for the optimizer.
     """
 
     def __init__(self, params, bucket_mb: float = 32.0, process_group=None):
@@ -166,68 +168,79 @@ class GradAllReducer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         dev = self.params[0].device
-        self.sync = True             # False: accumulate locally only (gradient accumulation / single-rank checks)
+        self.sync = True             # False: no exchange (single-rank checks); finish() still packs the buffer
         self.flat = None
         if self.world == 1:          # nothing to exchange: plain per-parameter gradients, dropped between steps
             return
         total = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.buckets = []            # (start, end, n_params)
+        self.buckets = []            # (start, end, [params])
         self._bucket_of = {}
-        order = list(reversed(self.params))
+        self._view = {}
         limit = int(bucket_mb * (1 << 20) / 4)
-        off, start, count = 0, 0, 0
-        for p in order:
+        off, start, members = 0, 0, []
+        for p in reversed(self.params):
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
+            self._view[p] = self.flat[off:off + n].view_as(p)
             self._bucket_of[p] = len(self.buckets)
+            members.append(p)
             off += n
-            count += 1
             if off - start >= limit:
-                self.buckets.append((start, off, count))
-                start, count = off, 0
-        if count:
-            self.buckets.append((start, off, count))
+                self.buckets.append((start, off, members))
+                start, members = off, []
+        if members:
+            self.buckets.append((start, off, members))
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._handles = []
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
 
+    def _pack(self, b: int) -> None:
+        """Gradients of bucket b -> their slices of the flat buffer (one multi-tensor copy; missing ones stay zero)."""
+        have = [p for p in self.buckets[b][2] if p.grad is not None and p.grad.data_ptr() != self._view[p].data_ptr()]
+        if have:
+            torch._foreach_copy_([self._view[p] for p in have], [p.grad for p in have])
+
     def _launch(self, b: int) -> None:
         if self._launched[b]:
             return
         self._launched[b] = True
-        s, e, _ = self.buckets[b]
-        self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._pack(b)
+        if self.sync:
+            s, e, _ = self.buckets[b]
+            self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def _hook(self, p) -> None:
         if not self.sync:
             return
         b = self._bucket_of[p]
         self._ready[b] += 1
-        if self._ready[b] == self.buckets[b][2]:
+        if self._ready[b] == len(self.buckets[b][2]):
             self._launch(b)
 
     def zero_grad(self) -> None:
+        for p in self.params:
+            p.grad = None
         if self.flat is None:
-            for p in self.params:
-                p.grad = None
             return
         self.flat.zero_()
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
 
     def finish(self) -> None:
-        """Flush incomplete buckets, wait for all reductions, average."""
-        if self.world == 1 or not self.sync:
+        """Flush incomplete buckets, wait for all reductions, average, expose the buffer slices as ``.grad``."""
+        if self.flat is None:
             return
         for b in range(len(self.buckets)):
             self._launch(b)
         for h in self._handles:
             h.wait()
         self._handles = []
-        self.flat.mul_(1.0 / self.world)
+        if self.sync:
+            self.flat.mul_(1.0 / self.world)
+        for p in self.params:
+            p.grad = self._view[p]
 
 
 class TrainStep:

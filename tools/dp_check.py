@@ -39,6 +39,7 @@ for shard in range(world):
     model.load_state_dict(sd0)
     red.zero_grad()
     grads_for(shard)
+    red.finish()                       # sync off: packs the local gradients into the buffer, no exchange
     ref += red.flat
 red.sync = True
 ref /= world
