@@ -152,7 +152,7 @@ def ncu_traffic() -> dict:
 
 
 def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: str, pk: dict, p_drop: float,
-                 slots: int = 6, n_rows: int = 0):
+                 slots: int = 6, n_rows: int = 0, act_bytes: int = 4):
     """Per-kernel-family algorithmic bytes / flops per launch and achieved rates.
     `slots` = operand blocks per node (6 relations, or 3 in the structured layout), `n_rows` = GEMM rows (padded)."""
     r = slots
@@ -161,13 +161,14 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
     s = 2 if precision == "bf16" else 8        # bytes per GEMM-operand element (bf16, or TF32 hi+lo fp32 pair)
     s_da = 2 if precision == "bf16" else 4
     eb = 8 if p_drop > 0 else 4
+    ab = act_bytes                          # activation storage between the kernels of a stack (x, out, y, gy, gx)
     parts = 1184 * d * 4                    # per-item partial rows of the edge-table gradient
     algo = {
-        "pb_agg_fwd": ("hbm", n * d * 4 + eb * e + 4 * (n * r + 1) + 128 * d + n * k * s),
-        "pb_agg_bwd": ("hbm", n * k * s_da + 2 * n * d * 4 + 16 * e + 4 * (n + 1) + n * d * 4 + 128 * d + parts),
-        "pb_bn_stats": ("hbm", n * d * 4),
-        "pb_bn_relu_res_fwd": ("hbm", 3 * n * d * 4),
-        "pb_bn_relu_res_bwd": ("hbm", 4 * n * d * 4 + n * d * s),
+        "pb_agg_fwd": ("hbm", n * d * ab + eb * e + 4 * (n * r + 1) + 128 * d + n * k * s),
+        "pb_agg_bwd": ("hbm", n * k * s_da + 2 * n * d * ab + 16 * e + 4 * (n + 1) + n * d * ab + 128 * d + parts),
+        "pb_bn_stats": ("hbm", n * d * ab),
+        "pb_bn_relu_res_fwd": ("hbm", 3 * n * d * ab),
+        "pb_bn_relu_res_bwd": ("hbm", 4 * n * d * ab + n * d * s),
         "pb_rgcn_gemm_fwd": ("tensor", 2 * n_rows * k * d),          # executed flops (structured: 4d-wide operand)
         "pb_rgcn_gemm_bwd_data": ("tensor", 2 * n_rows * k * d),
         "pb_rgcn_gemm_bwd_weight": ("tensor", 2 * n_rows * k * d),
@@ -315,7 +316,9 @@ def main():
         st = graph0.structured if pb.ops.structured_enabled() else None
         rows = kernel_table(summary, int(n_nodes), int(n_edges), MODEL_CFG["d"], args.steps, args.precision, pk,
                             args.gcl_dropout, slots=3 if st is not None else 6,
-                            n_rows=st.n_padded if st is not None else int(n_nodes))
+                            n_rows=st.n_padded if st is not None else int(n_nodes),
+                            act_bytes=2 if (args.precision == "bf16" and st is not None
+                                            and pb.ops.bf16_activations_enabled()) else 4)
         ours_ms = sum(v["ms"] for v in summary.values()) / args.steps
         top = next((r for r in rows if r["frac"] is not None), None)
         hbm_rows = [r for r in rows if r["bound"] == "hbm"]
@@ -344,6 +347,8 @@ def main():
                        "gnn_n_layers": 8, "nodes_per_gpu": int(n_nodes), "edges_per_gpu": int(n_edges),
                        "gcl_dropout": args.gcl_dropout, "parallelism": f"dp{world}",
                        "operand_layout": "structured 4d (track-relation-sorted)" if st is not None else "generic 7d",
+                       "activation_storage": "bf16 between the kernels of a GCN stack, fp32 arithmetic"
+                       if (args.precision == "bf16" and st is not None and pb.ops.bf16_activations_enabled()) else "fp32",
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "step": "device graph build + fwd + loss + bwd + NCCL grad all-reduce + Adam"},
             "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms / args.steps,

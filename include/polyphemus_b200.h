@@ -172,13 +172,18 @@ int pb_edge_table_bwd(const float* dtable_partials, const int32_t* dist_item_ptr
  *   (2) the rows of q_buf are summed per timestep distance through dist_perm / dist_items (fixed order) into
  *       dtable_partials f32 [PB_DIST_ITEMS, d], which pb_edge_table_bwd finishes.
  * ---------------------------------------------------------------------------------------------- */
+/* act_dtype (PB_F32 | PB_BF16) = storage of the activations that travel between the kernels of a stack: node features
+ * x / y, the pre-BatchNorm GEMM output `out`, and the gradients gy / gx. PB_F32 is the API dtype (reference tensors are
+ * fp32); PB_BF16 is what the throughput mode's GCN stacks keep between layers (the reference holds them in fp16 under
+ * autocast, training.py:137). Arithmetic is fp32 in both; row strides are in elements. */
 size_t pb_dropout_bits_bytes(int64_t n_edges, int32_t d);
 int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, void* keep_bits, pb_stream_t stream);
-int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, void* a_hi, void* a_lo,
-               int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, pb_stream_t stream);
-int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
-               int64_t ldda, int32_t dtype, const float* gy_res, float* gx, void* q_buf, float* dtable_partials,
-               const void* keep_bits, float p_drop, pb_stream_t stream);
+int pb_agg_fwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table, void* a_hi, void* a_lo,
+               int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, int32_t act_dtype,
+               pb_stream_t stream);
+int pb_agg_bwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table, const void* d_a,
+               int64_t ldda, int32_t dtype, const void* gy_res, void* gx, void* q_buf, float* dtable_partials,
+               const void* keep_bits, float p_drop, int32_t act_dtype, pb_stream_t stream);
 int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep /*[E,d]*/,
                     pb_stream_t stream);
 
@@ -196,8 +201,8 @@ int pb_weight_prep(const float* weight, const float* root, int32_t n_relations, 
  * flops, because a node only ever receives TRACK edges of one relation. k is then 4*d while the weight operands
  * keep their full (R+1)*d extent. */
 int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
-                     const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
-                     int32_t k, const pb_groups_t* groups, int32_t dtype, pb_stream_t stream);
+                     const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                     int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype, pb_stream_t stream);
 /* dA [M,K] = g[M,d] @ Wcat^T.  g_* is the GEMM-operand copy of the output gradient (bf16, or f32 hi/lo);
  * dA is bf16 (PB_BF16) or f32 (PB_F32). */
 int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
@@ -232,23 +237,25 @@ int pb_gemm_f32_check(const float* a, int64_t lda, const float* b, int64_t ldb, 
 size_t pb_bn_workspace_bytes(int64_t m, int32_t d);
 /* bn_coef f32 [3,d] = {mean, scale = gamma*rstd, beta}; save_mean_rstd f32 [2,d];
  * running_mean/var updated in place when not NULL. */
-int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups, const float* gamma,
+int pb_bn_stats(const void* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups, const float* gamma,
                 const float* beta, float eps, float momentum, float* running_mean, float* running_var,
-                float* save_mean_rstd, float* bn_coef, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+                float* save_mean_rstd, float* bn_coef, void* workspace, size_t workspace_bytes, int32_t act_dtype,
+                pb_stream_t stream);
 int pb_bn_prepare_eval(const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, int32_t d, float* bn_coef,
                        pb_stream_t stream);
 /* y = x_res + relu((out-mean)*scale + beta)   (x_res may be NULL: y = relu(...)); apply_relu=0 skips the ReLU */
-int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef,
-                       float* y, int64_t m, int32_t d, const pb_groups_t* groups, int32_t apply_relu,
-                       pb_stream_t stream);
+int pb_bn_relu_res_fwd(const void* out, int64_t ldo, const void* x_res, const float* bn_coef,
+                       void* y, int64_t m, int32_t d, const pb_groups_t* groups, int32_t apply_relu,
+                       int32_t act_dtype, pb_stream_t stream);
 /* Backward of y = x + relu(bn(out)) wrt out (training statistics):
  *   g_out f32 [m,d] (+ GEMM-operand copies g_hi/g_lo in `dtype`), g_gamma, g_beta, g_bias(=colsum g_out).
  *   The residual branch gradient is gy itself (consumed by pb_agg_bwd as gy_res). */
-int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
+int pb_bn_relu_res_bwd(const void* gy, const void* out, int64_t ldo, const float* gamma,
                        const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
                        const pb_groups_t* groups, int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma,
-                       float* g_beta, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);
+                       float* g_beta, float* g_bias, void* workspace, size_t workspace_bytes, int32_t act_dtype,
+                       pb_stream_t stream);
 /* Operand conversion for a plain GCL (no BN): g f32 [m,d] -> g_hi/g_lo in `dtype`, and g_bias = colsum. */
 int pb_grad_prep(const float* g, int64_t ldg_in, int64_t m, int32_t d, int32_t dtype, void* g_hi, void* g_lo,
                  int64_t ldg, float* g_bias, void* workspace, size_t workspace_bytes, pb_stream_t stream);

@@ -55,12 +55,13 @@ SIGNATURES = {
     "pb_edge_table_bwd": (c_int, [_P, _P, c_int32, _P, _P, _P]),
     "pb_dropout_bits_bytes": (c_size_t, [c_int64, c_int32]),
     "pb_dropout_bits": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
-    "pb_agg_fwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, c_float, _P]),
-    "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, _P]),
+    "pb_agg_fwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, _P, c_int64, c_int32, _P, c_float, c_int32, _P]),
+    "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_int32,
+                           _P]),
     "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
-                                 POINTER(GroupsStruct), c_int32, _P]),
+                                 POINTER(GroupsStruct), c_int32, c_int32, _P]),
     "pb_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
     "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
                                       POINTER(GroupsStruct), c_int32, _P]),
@@ -71,11 +72,11 @@ SIGNATURES = {
                                   c_int32, _P]),
     "pb_bn_workspace_bytes": (c_size_t, [c_int64, c_int32]),
     "pb_bn_stats": (c_int, [_P, c_int64, c_int64, c_int32, POINTER(GroupsStruct), _P, _P, c_float, c_float, _P, _P, _P, _P,
-                            _P, c_size_t, _P]),
+                            _P, c_size_t, c_int32, _P]),
     "pb_bn_prepare_eval": (c_int, [_P, _P, _P, _P, c_float, c_int32, _P, _P]),
-    "pb_bn_relu_res_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, POINTER(GroupsStruct), c_int32, _P]),
+    "pb_bn_relu_res_fwd": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int32, POINTER(GroupsStruct), c_int32, c_int32, _P]),
     "pb_bn_relu_res_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int32, POINTER(GroupsStruct), c_int32, _P, _P,
-                                   c_int64, _P, _P, _P, _P, c_size_t, _P]),
+                                   c_int64, _P, _P, _P, _P, c_size_t, c_int32, _P]),
     "pb_grad_prep": (c_int, [_P, c_int64, c_int64, c_int32, c_int32, _P, _P, c_int64, _P, _P, c_size_t, _P]),
     "pb_chord_embed_fwd": (c_int, [_P, c_int64, c_int32, c_int32, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P, c_int64,
                                    c_int64, _P]),

@@ -155,10 +155,14 @@ class GCN(nn.Module):
         if st is not None and self.batch_norm and self.p == 0 and x.size(1) % 256 == 0 and x.is_cuda:
             # structured layout: nodes sorted by track relation, groups padded to the GEMM tile (zero rows), the
             # whole stack runs on [Np, d]; one gather in, one gather out
-            xp = ops.ScatterRowsFn.apply(x, st.pos, st.n_padded)
+            # bf16 mode: the stack keeps its activations (x, the pre-BatchNorm output, y and their gradients) in bf16
+            # between the kernels — 16-bit storage as under the reference's fp16 autocast, fp32 arithmetic inside
+            act_bf16 = (self.layers[0].precision or ops.get_precision()) == "bf16" and ops.bf16_activations_enabled()
+            xp = ops.ScatterRowsFn.apply(x.to(torch.bfloat16) if act_bf16 else x, st.pos, st.n_padded)
             for i, layer in enumerate(self.layers):
                 xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st)
-            return ops.GatherRowsFn.apply(xp, st.pos)
+            out = ops.GatherRowsFn.apply(xp, st.pos)
+            return out.float() if act_bf16 else out
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):
             residual = x

@@ -125,9 +125,9 @@ __device__ __forceinline__ void store_operand(void* a_hi, void* a_lo, size_t ele
 // CPL = float4 chunks per lane; EXACT: d == 128 * CPL (no tail predicates). One warp per destination node. The
 // node's R+1 segment offsets and its (<= 32 at a time) edge records are fetched by one coalesced load each and
 // broadcast with shuffles, so the only dependent round trip before the row gathers is that single record load.
-template <bool BF16, bool DROPOUT, int CPL, bool EXACT>
+template <bool BF16, bool DROPOUT, int CPL, bool EXACT, bool ABF>
 __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in_ptr, const int* __restrict__ in_edge,
-                                                      const int* __restrict__ in_eid, const float* __restrict__ x,
+                                                      const int* __restrict__ in_eid, const void* __restrict__ x,
                                                       const float* __restrict__ table, void* __restrict__ a_hi,
                                                       void* __restrict__ a_lo, int64_t lda, int64_t n_nodes, int d,
                                                       int n_rel, const uint16_t* __restrict__ keep_bits, float keep_scale,
@@ -148,11 +148,11 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
     uint32_t my_eid = 0;
     if constexpr (DROPOUT) my_eid = base + lane < end_all ? (uint32_t)__ldg(in_eid + base + lane) : 0u;
     // root block: the node's own features, converted to the operand dtype
-    const float* xrow = x + (size_t)v * d + 4 * lane;
+    const size_t xrow = (size_t)v * d + 4 * lane;
 #pragma unroll
     for (int j = 0; j < CPL; ++j)
       if (EXACT || lane + 32 * j < nchunk)
-        store_operand<BF16>(a_hi, a_lo, row + (size_t)n_rel * d + 4 * (lane + 32 * j), ldg4(xrow + 128 * j));
+        store_operand<BF16>(a_hi, a_lo, row + (size_t)n_rel * d + 4 * (lane + 32 * j), act_ld4<ABF>(x, xrow + 128 * j));
     int e = beg_all;
     for (int r = 0; r < n_rel; ++r) {
       const int seg_end = __shfl_sync(kFull, my_ptr, r + 1);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
           if constexpr (DROPOUT) my_eid = base + lane < end_all ? (uint32_t)__ldg(in_eid + base + lane) : 0u;
         }
         const uint32_t pk = __shfl_sync(kFull, my_pk, e - base);
-        const float* srow = x + (size_t)(pk & 0x03FFFFFFu) * d + 4 * lane;
+        const size_t srow = (size_t)(pk & 0x03FFFFFFu) * d + 4 * lane;
         const float* trow = table + (size_t)(pk >> 26) * d + 4 * lane;
         uint32_t kw[G16];
         if constexpr (DROPOUT) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
           if (EXACT || lane + 32 * j < nchunk) {
-            const float4 xs = ldg4(srow + 128 * j);
+            const float4 xs = act_ld4<ABF>(x, srow + 128 * j);
             const float4 t = ldg4(trow + 128 * j);
             float4 m = make_float4(fmaxf(xs.x * t.x, 0.f), fmaxf(xs.y * t.y, 0.f), fmaxf(xs.z * t.z, 0.f),
                                    fmaxf(xs.w * t.w, 0.f));
@@ -246,11 +246,11 @@ __device__ __forceinline__ void store_q(void* q, size_t elem_off, float4 v) {
 // (1) Scatter-by-source without atomics: one warp per source node u gathers the gradients of the segments its
 // out-edges feed (same shape as the forward: coalesced record load, shuffles, 16-byte row gathers, full occupancy)
 // and emits, per out-edge position, the row q_e = ds_e * x[u] that the edge-table gradient needs.
-template <bool BF16, bool DROPOUT, int CPL, bool EXACT>
+template <bool BF16, bool DROPOUT, int CPL, bool EXACT, bool ABF>
 __global__ void __launch_bounds__(256, (BF16 && CPL <= 4) ? 3 : 1) agg_bwd_dx_kernel(
-    const int* __restrict__ out_ptr, const int4* __restrict__ out_rec, const float* __restrict__ x,
-    const float* __restrict__ table, const void* __restrict__ d_a, int64_t ldda, const float* __restrict__ gy_res,
-    float* __restrict__ gx, void* __restrict__ q_buf, int64_t n_nodes, int d, int n_rel,
+    const int* __restrict__ out_ptr, const int4* __restrict__ out_rec, const void* __restrict__ x,
+    const float* __restrict__ table, const void* __restrict__ d_a, int64_t ldda, const void* __restrict__ gy_res,
+    void* __restrict__ gx, void* __restrict__ q_buf, int64_t n_nodes, int d, int n_rel,
     const uint16_t* __restrict__ keep_bits, float keep_scale, const int* __restrict__ node_order) {
   constexpr uint32_t kFull = 0xffffffffu;
   constexpr int G16 = (CPL + 3) / 4;
@@ -268,10 +268,10 @@ __global__ void __launch_bounds__(256, (BF16 && CPL <= 4) ? 3 : 1) agg_bwd_dx_ke
     for (int j = 0; j < CPL; ++j) {
       if (EXACT || lane + 32 * j < nchunk) {
         const size_t c4 = 4 * (size_t)(lane + 32 * j);
-        xu[j] = ldg4(x + (size_t)u * d + c4);
+        xu[j] = act_ld4<ABF>(x, (size_t)u * d + c4);
         acc[j] = load_grad4<BF16>(d_a, (size_t)u * ldda + (size_t)n_rel * d + c4);   // root branch
         if (gy_res) {
-          const float4 r = ld_stream4(gy_res + (size_t)u * d + c4);                   // residual branch
+          const float4 r = act_ld4_stream<ABF>(gy_res, (size_t)u * d + c4);           // residual branch
           acc[j].x += r.x; acc[j].y += r.y; acc[j].z += r.z; acc[j].w += r.w;
         }
       }
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(256, (BF16 && CPL <= 4) ? 3 : 1) agg_bwd_dx_ke
     }
 #pragma unroll
     for (int j = 0; j < CPL; ++j)
-      if (EXACT || lane + 32 * j < nchunk) st_stream4(gx + (size_t)u * d + 4 * (lane + 32 * j), acc[j]);
+      if (EXACT || lane + 32 * j < nchunk) act_st4_stream<ABF>(gx, (size_t)u * d + 4 * (lane + 32 * j), acc[j]);
   }
 }
 
@@ -429,8 +429,8 @@ extern "C" int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_
   return PB_OK;
 }
 
-template <bool BF16, bool DROP>
-static int launch_agg_fwd(const pb_csr_t* g, const float* x, int d, const float* table, void* a_hi, void* a_lo,
+template <bool BF16, bool DROP, bool ABF>
+static int launch_agg_fwd(const pb_csr_t* g, const void* x, int d, const float* table, void* a_hi, void* a_lo,
                           int64_t lda, const uint16_t* bits, float scale, cudaStream_t st) {
   const int cpl = (d + 127) / 128;
   const bool exact = d % 128 == 0 && (cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8);
@@ -438,7 +438,7 @@ static int launch_agg_fwd(const pb_csr_t* g, const float* x, int d, const float*
   const int64_t want = (g->n_nodes * 32 + threads - 1) / threads;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8 * 4));
 #define PB_AGG_FWD(CPL, EX)                                                                                      \
-  agg_fwd_kernel<BF16, DROP, CPL, EX><<<grid, threads, 0, st>>>(g->in_ptr, g->in_edge, g->in_eid, x, table, a_hi, \
+  agg_fwd_kernel<BF16, DROP, CPL, EX, ABF><<<grid, threads, 0, st>>>(g->in_ptr, g->in_edge, g->in_eid, x, table, a_hi, \
                                                                 a_lo, lda, g->n_nodes, d, g->n_relations, bits, scale, \
                                                                 g->node_order)
   if (exact) {
@@ -457,10 +457,19 @@ static int launch_agg_fwd(const pb_csr_t* g, const float* x, int d, const float*
   return PB_OK;
 }
 
-extern "C" int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, void* a_hi, void* a_lo,
-                          int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, pb_stream_t stream) {
+// bf16 activation storage goes with the bf16 operand mode only
+static int check_act_dtype(int32_t dtype, int32_t act_dtype, const char* who) {
+  PB_REQUIRE(act_dtype == PB_F32 || (act_dtype == PB_BF16 && dtype == PB_BF16),
+             "%s: act_dtype %d (bf16 activations need the PB_BF16 operand mode)", who, act_dtype);
+  return PB_OK;
+}
+
+extern "C" int pb_agg_fwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table, void* a_hi, void* a_lo,
+                          int64_t lda, int32_t dtype, const void* keep_bits, float p_drop, int32_t act_dtype,
+                          pb_stream_t stream) {
   int rc = check_csr(csr, d, "pb_agg_fwd");
   if (rc) return rc;
+  if ((rc = check_act_dtype(dtype, act_dtype, "pb_agg_fwd"))) return rc;
   PB_REQUIRE(x && table && a_hi, "pb_agg_fwd: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (dtype == PB_F32 && a_lo), "pb_agg_fwd: PB_F32 needs a_lo");
   PB_REQUIRE(lda >= (int64_t)(csr->n_relations + 1) * d && lda % 8 == 0, "pb_agg_fwd: bad lda");
@@ -470,16 +479,19 @@ extern "C" int pb_agg_fwd(const pb_csr_t* csr, const float* x, int32_t d, const 
   cudaStream_t st = as_stream(stream);
   const uint16_t* bits = p_drop > 0.f ? reinterpret_cast<const uint16_t*>(keep_bits) : nullptr;
   const float scale = 1.f / (1.f - p_drop);
+  if (dtype == PB_BF16 && act_dtype == PB_BF16)
+    return bits ? launch_agg_fwd<true, true, true>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st)
+                : launch_agg_fwd<true, false, true>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
   if (dtype == PB_BF16)
-    return bits ? launch_agg_fwd<true, true>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st)
-                : launch_agg_fwd<true, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
-  return bits ? launch_agg_fwd<false, true>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st)
-              : launch_agg_fwd<false, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
+    return bits ? launch_agg_fwd<true, true, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st)
+                : launch_agg_fwd<true, false, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
+  return bits ? launch_agg_fwd<false, true, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st)
+              : launch_agg_fwd<false, false, false>(csr, x, d, table, a_hi, a_lo, lda, bits, scale, st);
 }
 
-template <bool BF16, bool DROP>
-static int launch_agg_bwd(const pb_csr_t* g, const float* x, int d, const float* table, const void* d_a, int64_t ldda,
-                          const float* gy_res, float* gx, void* q_buf, float* dtp, const uint16_t* bits, float scale,
+template <bool BF16, bool DROP, bool ABF>
+static int launch_agg_bwd(const pb_csr_t* g, const void* x, int d, const float* table, const void* d_a, int64_t ldda,
+                          const void* gy_res, void* gx, void* q_buf, float* dtp, const uint16_t* bits, float scale,
                           cudaStream_t st) {
   const int cpl = (d + 127) / 128;
   const bool exact = d % 128 == 0 && (cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8);
@@ -488,7 +500,7 @@ static int launch_agg_bwd(const pb_csr_t* g, const float* x, int d, const float*
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8 * 4));
   const int4* recs = reinterpret_cast<const int4*>(g->out_rec);
 #define PB_AGG_BWD(CPL, EX)                                                                                        \
-  agg_bwd_dx_kernel<BF16, DROP, CPL, EX><<<grid, threads, 0, st>>>(g->out_ptr, recs, x, table, d_a, ldda, gy_res,   \
+  agg_bwd_dx_kernel<BF16, DROP, CPL, EX, ABF><<<grid, threads, 0, st>>>(g->out_ptr, recs, x, table, d_a, ldda, gy_res,   \
                                                                    gx, q_buf, g->n_nodes, d, g->n_relations, bits, scale, \
                                                                    g->node_order)
   if (exact) {
@@ -513,11 +525,13 @@ static int launch_agg_bwd(const pb_csr_t* g, const float* x, int d, const float*
   return PB_OK;
 }
 
-extern "C" int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const float* table, const void* d_a,
-                          int64_t ldda, int32_t dtype, const float* gy_res, float* gx, void* q_buf,
-                          float* dtable_partials, const void* keep_bits, float p_drop, pb_stream_t stream) {
+extern "C" int pb_agg_bwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table, const void* d_a,
+                          int64_t ldda, int32_t dtype, const void* gy_res, void* gx, void* q_buf,
+                          float* dtable_partials, const void* keep_bits, float p_drop, int32_t act_dtype,
+                          pb_stream_t stream) {
   int rc = check_csr(csr, d, "pb_agg_bwd");
   if (rc) return rc;
+  if ((rc = check_act_dtype(dtype, act_dtype, "pb_agg_bwd"))) return rc;
   PB_REQUIRE(x && table && d_a && gx && q_buf && dtable_partials, "pb_agg_bwd: null pointer");
   PB_REQUIRE(csr->dist_perm && csr->dist_items && csr->dist_item_ptr, "pb_agg_bwd: CSR plan lacks the distance grouping");
   PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "pb_agg_bwd: bad dtype");
@@ -527,11 +541,12 @@ extern "C" int pb_agg_bwd(const pb_csr_t* csr, const float* x, int32_t d, const 
   cudaStream_t st = as_stream(stream);
   const uint16_t* bits = p_drop > 0.f ? reinterpret_cast<const uint16_t*>(keep_bits) : nullptr;
   const float scale = 1.f / (1.f - p_drop);
-  if (dtype == PB_BF16)
-    return bits ? launch_agg_bwd<true, true>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st)
-                : launch_agg_bwd<true, false>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st);
-  return bits ? launch_agg_bwd<false, true>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st)
-              : launch_agg_bwd<false, false>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st);
+#define PB_AGG_BWD_CALL(BF, DR, AB) \
+  launch_agg_bwd<BF, DR, AB>(csr, x, d, table, d_a, ldda, gy_res, gx, q_buf, dtable_partials, bits, scale, st)
+  if (dtype == PB_BF16 && act_dtype == PB_BF16) return bits ? PB_AGG_BWD_CALL(true, true, true) : PB_AGG_BWD_CALL(true, false, true);
+  if (dtype == PB_BF16) return bits ? PB_AGG_BWD_CALL(true, true, false) : PB_AGG_BWD_CALL(true, false, false);
+  return bits ? PB_AGG_BWD_CALL(false, true, false) : PB_AGG_BWD_CALL(false, false, false);
+#undef PB_AGG_BWD_CALL
 }
 
 extern "C" int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep,

@@ -65,7 +65,9 @@ static inline int col_ctas(int64_t m) {
 
 // Each CTA reduces a contiguous row range for every column; thread = (row group, float4 column chunk).
 // partials: [gridDim.x][NV][d]
-template <int NV, class Load>
+// UNROLL rows of loads in flight per thread (the cheap statistics pass takes 4; the backward passes carry too many live
+// values for that and slow down).
+template <int NV, int UNROLL, class Load>
 __device__ __forceinline__ void column_partials(const RowMap& rm, int d, float* __restrict__ partials, Load load) {
   const int64_t m = rm.total;   // valid rows; the loader receives padded row indices
   extern __shared__ float red[];  // [NV][nrg][d]
@@ -88,7 +90,8 @@ __device__ __forceinline__ void column_partials(const RowMap& rm, int d, float* 
       // keep the row-group phase of the plain loop: thread row-group rg owns compact rows r0 + rg + i * nrg
       int64_t r = r0 + rg;
       if (r < lo) r += (lo - r + nrg - 1) / nrg * nrg;
-      for (; r < hi; r += nrg) {
+#pragma unroll UNROLL
+      for (; r < hi; r += nrg) {   // the additions stay in row order
         float4 v[NV];
         load(r + shift, c, v);
 #pragma unroll
@@ -143,13 +146,14 @@ __device__ __forceinline__ bool finalize_sums(const float* __restrict__ partials
 }
 
 // ------------------------------------------------------------------------------------------------ forward stats
-__global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const float* __restrict__ out, int64_t ldo,
+template <bool ABF>
+__global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const void* __restrict__ out, int64_t ldo,
                                                                       const RowMap rm, int d,
                                                                       float* __restrict__ partials) {
-  const float* shift_row = out + (size_t)rm.padded(0) * ldo;
-  column_partials<2>(rm, d, partials, [&](int64_t r, int c, float4* v) {
-    const float4 x = ld_stream4(out + (size_t)r * ldo + 4 * c);
-    const float4 k = ldg4(shift_row + 4 * c);  // shift = first valid row (exact, cancels in the variance)
+  const size_t shift_off = (size_t)rm.padded(0) * ldo;
+  column_partials<2, 4>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 x = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
+    const float4 k = act_ld4<ABF>(out, shift_off + 4 * c);  // shift = first valid row (exact, cancels in the variance)
     const float4 dlt = make_float4(x.x - k.x, x.y - k.y, x.z - k.z, x.w - k.w);
     v[0] = dlt;
     v[1] = make_float4(dlt.x * dlt.x, dlt.y * dlt.y, dlt.z * dlt.z, dlt.w * dlt.w);
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const flo
 }
 
 __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int n_part,
-                                         const float* __restrict__ shift_row, int64_t m, int d,
+                                         const void* __restrict__ shift_row, bool abf, int64_t m, int d,
                                          const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float eps, float momentum,
                                          float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -167,7 +171,7 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int
   const int c = blockIdx.x * 32 + threadIdx.x;
   const double s1 = s[0], s2 = s[1];
   const double n = (double)m;
-  const double mean = (double)shift_row[c] + s1 / n;
+  const double mean = (double)act_ld1(shift_row, c, abf) + s1 / n;
   double var = (s2 - s1 * s1 / n) / n;
   if (var < 0.0) var = 0.0;
   const float meanf = (float)mean, varf = (float)var;
@@ -195,43 +199,45 @@ __global__ void bn_prepare_eval_kernel(const float* __restrict__ gamma, const fl
 }
 
 // ------------------------------------------------------------------------------------------------ forward apply
-template <bool RELU, bool RES>
-__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ out, int64_t ldo,
-                                                      const float* __restrict__ x_res, const float* __restrict__ coef,
-                                                      float* __restrict__ y, int64_t m, int d, const RowMap rm) {
+template <bool RELU, bool RES, bool ABF>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const void* __restrict__ out, int64_t ldo,
+                                                      const void* __restrict__ x_res, const float* __restrict__ coef,
+                                                      void* __restrict__ y, int64_t m, int d, const RowMap rm) {
   const int nchunk = d >> 2;
   const int64_t total = m * nchunk;
+#pragma unroll 2
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nchunk;
     const int c = (int)(i - r * nchunk);
     if (rm.n > 1 && !rm.valid(r)) {   // padding row of the structured layout stays zero
-      st_stream4(y + (size_t)r * d + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
+      act_st4_stream<ABF>(y, (size_t)r * d + 4 * c, make_float4(0.f, 0.f, 0.f, 0.f));
       continue;
     }
-    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+    const float4 o = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
     float4 z = make_float4((o.x - mu.x) * sc.x + be.x, (o.y - mu.y) * sc.y + be.y, (o.z - mu.z) * sc.z + be.z,
                            (o.w - mu.w) * sc.w + be.w);
     if (RELU) { z.x = fmaxf(z.x, 0.f); z.y = fmaxf(z.y, 0.f); z.z = fmaxf(z.z, 0.f); z.w = fmaxf(z.w, 0.f); }
     if (RES) {
-      const float4 xr = ld_stream4(x_res + (size_t)r * d + 4 * c);
+      const float4 xr = act_ld4_stream<ABF>(x_res, (size_t)r * d + 4 * c);
       z.x += xr.x; z.y += xr.y; z.z += xr.z; z.w += xr.w;
     }
-    st_stream4(y + (size_t)r * d + 4 * c, z);
+    act_st4_stream<ABF>(y, (size_t)r * d + 4 * c, z);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ backward
 // pass 1: g_beta = sum gz, g_gamma = sum gz * xhat   with gz = gy * 1[(out-mean)*scale+beta > 0]
-__global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const float* __restrict__ gy,
-                                                                    const float* __restrict__ out, int64_t ldo,
+template <bool ABF>
+__global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const void* __restrict__ gy,
+                                                                    const void* __restrict__ out, int64_t ldo,
                                                                     const float* __restrict__ coef,
                                                                     const float* __restrict__ mean_rstd,
                                                                     const RowMap rm, int d,
                                                                     float* __restrict__ partials) {
-  column_partials<2>(rm, d, partials, [&](int64_t r, int c, float4* v) {
-    const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
-    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+  column_partials<2, 1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 g = act_ld4_stream<ABF>(gy, (size_t)r * d + 4 * c);
+    const float4 o = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
     const float4 rs = ldg4(mean_rstd + d + 4 * c);
     const float4 ctr = make_float4(o.x - mu.x, o.y - mu.y, o.z - mu.z, o.w - mu.w);
@@ -269,16 +275,16 @@ __device__ __forceinline__ void store_g(void* g_hi, void* g_lo, size_t off, floa
 
 // pass 2: g_out = scale * (gz - g_beta/m - xhat * g_gamma/m), written as the GEMM operand; column sums of
 // g_out (the bias gradient of the layer feeding this BatchNorm) leave as partials.
-template <bool BF16>
+template <bool BF16, bool ABF>
 __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(
-    const float* __restrict__ gy, const float* __restrict__ out, int64_t ldo, const float* __restrict__ coef,
+    const void* __restrict__ gy, const void* __restrict__ out, int64_t ldo, const float* __restrict__ coef,
     const float* __restrict__ mean_rstd, const float* __restrict__ g_gamma, const float* __restrict__ g_beta,
     const RowMap rm, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg,
     float* __restrict__ partials) {
   const float inv_m = 1.f / (float)rm.total;
-  column_partials<1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
-    const float4 g = ld_stream4(gy + (size_t)r * d + 4 * c);
-    const float4 o = ld_stream4(out + (size_t)r * ldo + 4 * c);
+  column_partials<1, 1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+    const float4 g = act_ld4_stream<ABF>(gy, (size_t)r * d + 4 * c);
+    const float4 o = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
     const float4 rs = ldg4(mean_rstd + d + 4 * c);
     const float4 gg = ldg4(g_gamma + 4 * c), gb = ldg4(g_beta + 4 * c);
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(kColThreads) grad_prep_kernel(const float* __r
   RowMap rm;
   rm.n = 1; rm.total = m; rm.cum[0] = 0; rm.cum[1] = rm.cum[2] = rm.cum[3] = rm.cum[4] = m;
   rm.start[0] = rm.start[1] = rm.start[2] = rm.start[3] = 0;
-  column_partials<1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+  column_partials<1, 1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 x = ld_stream4(g + (size_t)r * ldg_in + 4 * c);
     store_g<BF16>(g_hi, g_lo, (size_t)r * ldg + 4 * c, x);
     v[0] = x;
@@ -326,10 +332,19 @@ extern "C" size_t pb_bn_workspace_bytes(int64_t m, int32_t d) {
   return align_up((size_t)col_ctas(m) * 2 * d * sizeof(float), 256);
 }
 
-extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups,
+static int check_act(int32_t act_dtype, int64_t ld, const char* who) {
+  PB_REQUIRE(act_dtype == PB_F32 || act_dtype == PB_BF16, "%s: act_dtype %d", who, act_dtype);
+  PB_REQUIRE(ld % 4 == 0, "%s: row stride must be a multiple of 4 elements", who);
+  return PB_OK;
+}
+
+extern "C" int pb_bn_stats(const void* out, int64_t ldo, int64_t m, int32_t d, const pb_groups_t* groups,
                            const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                            float* running_var, float* save_mean_rstd, float* bn_coef, void* workspace,
-                           size_t workspace_bytes, pb_stream_t stream) {
+                           size_t workspace_bytes, int32_t act_dtype, pb_stream_t stream) {
+  if (int rca = check_act(act_dtype, ldo, "pb_bn_stats")) return rca;
+  const bool abf = act_dtype == PB_BF16;
+  const size_t esz = abf ? 2 : 4;
   int rc = check_md(m, d, "pb_bn_stats");
   if (rc) return rc;
   PB_REQUIRE(out && gamma && beta && save_mean_rstd && bn_coef && workspace, "pb_bn_stats: null pointer");
@@ -341,12 +356,14 @@ extern "C" int pb_bn_stats(const float* out, int64_t ldo, int64_t m, int32_t d, 
   PB_REQUIRE(mv > 0 && mv <= m, "pb_bn_stats: bad row groups");
   const int ctas = col_ctas(mv);
   float* partials = reinterpret_cast<float*>(workspace);
-  bn_stats_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, rm, d, partials);
+  if (abf) bn_stats_partial_kernel<true><<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, rm, d, partials);
+  else bn_stats_partial_kernel<false><<<ctas, kColThreads, col_smem(2, d), st>>>(out, ldo, rm, d, partials);
   PB_LAUNCH_CHECK();
-  const float* shift_row = out + (size_t)(rm.n > 0 ? rm.start[0] + 0 : 0) * ldo;   // == padded(0) when group 0 is non-empty
+  const char* base = static_cast<const char*>(out);
+  const void* shift_row = base + (size_t)(rm.n > 0 ? rm.start[0] + 0 : 0) * ldo * esz;   // == padded(0) when group 0 is non-empty
   for (int g = 0; g < rm.n; ++g)
-    if (rm.cum[g + 1] > rm.cum[g]) { shift_row = out + (size_t)rm.start[g] * ldo; break; }
-  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, shift_row, mv, d, gamma, beta, eps,
+    if (rm.cum[g + 1] > rm.cum[g]) { shift_row = base + (size_t)rm.start[g] * ldo * esz; break; }
+  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, shift_row, abf, mv, d, gamma, beta, eps,
                                                                            momentum, running_mean, running_var,
                                                                            save_mean_rstd, bn_coef);
   PB_LAUNCH_CHECK();
@@ -362,9 +379,10 @@ extern "C" int pb_bn_prepare_eval(const float* gamma, const float* beta, const f
   return PB_OK;
 }
 
-extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_res, const float* bn_coef, float* y,
+extern "C" int pb_bn_relu_res_fwd(const void* out, int64_t ldo, const void* x_res, const float* bn_coef, void* y,
                                   int64_t m, int32_t d, const pb_groups_t* groups, int32_t apply_relu,
-                                  pb_stream_t stream) {
+                                  int32_t act_dtype, pb_stream_t stream) {
+  if (int rca = check_act(act_dtype, ldo, "pb_bn_relu_res_fwd")) return rca;
   int rc = check_md(m, d, "pb_bn_relu_res_fwd");
   if (rc) return rc;
   PB_REQUIRE(out && bn_coef && y, "pb_bn_relu_res_fwd: null pointer");
@@ -373,22 +391,28 @@ extern "C" int pb_bn_relu_res_fwd(const float* out, int64_t ldo, const float* x_
   const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
   cudaStream_t st = as_stream(stream);
   const RowMap rm = make_rowmap(groups, m);
+#define PB_BN_APPLY(RELU, RES, ABF) \
+  bn_apply_kernel<RELU, RES, ABF><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm)
+#define PB_BN_APPLY_ACT(RELU, RES) \
+  do { if (act_dtype == PB_BF16) PB_BN_APPLY(RELU, RES, true); else PB_BN_APPLY(RELU, RES, false); } while (0)
   if (apply_relu) {
-    if (x_res) bn_apply_kernel<true, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
-    else bn_apply_kernel<true, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
+    if (x_res) PB_BN_APPLY_ACT(true, true); else PB_BN_APPLY_ACT(true, false);
   } else {
-    if (x_res) bn_apply_kernel<false, true><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
-    else bn_apply_kernel<false, false><<<grid, 256, 0, st>>>(out, ldo, x_res, bn_coef, y, m, d, rm);
+    if (x_res) PB_BN_APPLY_ACT(false, true); else PB_BN_APPLY_ACT(false, false);
   }
+#undef PB_BN_APPLY_ACT
+#undef PB_BN_APPLY
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
 
-extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo, const float* gamma,
+extern "C" int pb_bn_relu_res_bwd(const void* gy, const void* out, int64_t ldo, const float* gamma,
                                   const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
                                   const pb_groups_t* groups, int32_t dtype, void* g_hi, void* g_lo, int64_t ldg,
                                   float* g_gamma, float* g_beta, float* g_bias, void* workspace,
-                                  size_t workspace_bytes, pb_stream_t stream) {
+                                  size_t workspace_bytes, int32_t act_dtype, pb_stream_t stream) {
+  if (int rca = check_act(act_dtype, ldo, "pb_bn_relu_res_bwd")) return rca;
+  const bool abf = act_dtype == PB_BF16;
   int rc = check_md(m, d, "pb_bn_relu_res_bwd");
   if (rc) return rc;
   (void)gamma;
@@ -403,16 +427,17 @@ extern "C" int pb_bn_relu_res_bwd(const float* gy, const float* out, int64_t ldo
   PB_REQUIRE(mv > 0 && mv <= m, "pb_bn_relu_res_bwd: bad row groups");
   const int ctas = col_ctas(mv);
   float* partials = reinterpret_cast<float*>(workspace);
-  bn_bwd_partial_kernel<<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, rm, d, partials);
+  if (abf) bn_bwd_partial_kernel<true><<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, rm, d, partials);
+  else bn_bwd_partial_kernel<false><<<ctas, kColThreads, col_smem(2, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, rm, d, partials);
   PB_LAUNCH_CHECK();
   col_finalize_kernel<2><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_beta, g_gamma);
   PB_LAUNCH_CHECK();
-  if (dtype == PB_BF16)
-    bn_bwd_apply_kernel<true><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
-                                                                        g_beta, rm, d, g_hi, g_lo, ldg, partials);
-  else
-    bn_bwd_apply_kernel<false><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma,
-                                                                         g_beta, rm, d, g_hi, g_lo, ldg, partials);
+#define PB_BN_BWD_APPLY(BF, ABF)                                                                                     \
+  bn_bwd_apply_kernel<BF, ABF><<<ctas, kColThreads, col_smem(1, d), st>>>(gy, out, ldo, bn_coef, save_mean_rstd, g_gamma, \
+                                                                          g_beta, rm, d, g_hi, g_lo, ldg, partials)
+  if (dtype == PB_BF16) { if (abf) PB_BN_BWD_APPLY(true, true); else PB_BN_BWD_APPLY(true, false); }
+  else { if (abf) PB_BN_BWD_APPLY(false, true); else PB_BN_BWD_APPLY(false, false); }
+#undef PB_BN_BWD_APPLY
   PB_LAUNCH_CHECK();
   if (g_bias) {
     col_finalize_kernel<1><<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, d, g_bias, nullptr);

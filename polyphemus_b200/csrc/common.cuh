@@ -72,6 +72,41 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// ------------------------------------------------------------------ activation storage (fp32 or bf16 rows)
+// Node features x / y, the pre-BatchNorm output `out` and their gradients travel between the kernels of a stack either
+// as fp32 (the API dtype, PB_F32) or as bf16 (PB_BF16: the throughput mode's stacks keep them in 16 bits, as the
+// reference does under fp16 autocast). Arithmetic is fp32 either way; `elem` is an element offset, 4 elements a call.
+template <bool ABF>
+__device__ __forceinline__ float4 act_ld4(const void* base, size_t elem) {
+  if constexpr (ABF) {
+    const uint2 p = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(base) + elem));
+    const float2 a = unpack_bf16x2(p.x), b = unpack_bf16x2(p.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return ldg4(static_cast<const float*>(base) + elem);
+  }
+}
+template <bool ABF>
+__device__ __forceinline__ float4 act_ld4_stream(const void* base, size_t elem) {
+  if constexpr (ABF) {
+    const uint2 p = ld_stream2(static_cast<const __nv_bfloat16*>(base) + elem);
+    const float2 a = unpack_bf16x2(p.x), b = unpack_bf16x2(p.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  } else {
+    return ld_stream4(static_cast<const float*>(base) + elem);
+  }
+}
+template <bool ABF>
+__device__ __forceinline__ void act_st4_stream(void* base, size_t elem, float4 v) {
+  if constexpr (ABF)
+    st_stream2(static_cast<__nv_bfloat16*>(base) + elem, make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w)));
+  else
+    st_stream4(static_cast<float*>(base) + elem, v);
+}
+__device__ __forceinline__ float act_ld1(const void* base, size_t elem, bool abf) {
+  return abf ? __bfloat162float(static_cast<const __nv_bfloat16*>(base)[elem]) : static_cast<const float*>(base)[elem];
+}
+
 // TF32 split used by the PB_F32 tensor-core mode: hi keeps the top 19 bits (sign, 8 exp, 10 mantissa),
 // lo = v - hi is exact in fp32 and is itself truncated to TF32 by the tensor core (error <= 2^-21 |v|).
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }

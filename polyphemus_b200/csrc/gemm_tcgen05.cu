@@ -632,10 +632,14 @@ static int bwd_weight_splits(int64_t m, int d, int k, bool bf16) {
 using namespace pb;
 
 extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
-                                const void* wcat_t_lo, const float* bias, float* out, int64_t ldo, int64_t m, int32_t d,
-                                int32_t k, const pb_groups_t* groups, int32_t dtype, pb_stream_t stream) {
+                                const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                                int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype,
+                                pb_stream_t stream) {
   int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_fwd");
   if (rc) return rc;
+  PB_REQUIRE(act_dtype == PB_F32 || (act_dtype == PB_BF16 && dtype == PB_BF16),
+             "pb_rgcn_gemm_fwd: act_dtype %d (a bf16 output needs the PB_BF16 operand mode)", act_dtype);
+  const bool out_bf16 = act_dtype == PB_BF16;
   PB_REQUIRE(a_hi && wcat_t_hi && out, "pb_rgcn_gemm_fwd: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (a_lo && wcat_t_lo), "pb_rgcn_gemm_fwd: PB_F32 needs lo operands");
   PB_REQUIRE(lda >= k && lda % 8 == 0 && ldo >= d && ldo % 4 == 0, "pb_rgcn_gemm_fwd: bad leading dimension");
@@ -645,7 +649,7 @@ extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda,
   Operand a{a_hi, a_lo, m, k, lda, false};
   Operand b{wcat_t_hi, wcat_t_lo, d, kw, kw, false};
   cudaStream_t st = as_stream(stream);
-  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d)
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, out_bf16, bias, 1, 0, st, groups, 1, d)
                         : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d);
   return rc < 0 ? rc : PB_OK;
 }

@@ -49,6 +49,19 @@ def structured_enabled() -> bool:
     return _structured
 
 
+_bf16_activations = os.environ.get("PB200_BF16_ACT", "1") != "0"
+
+
+def set_bf16_activations(enabled: bool) -> None:
+    """bf16 mode only: keep the activations of a structured GCN stack in bf16 between its kernels (default) or in fp32."""
+    global _bf16_activations
+    _bf16_activations = bool(enabled)
+
+
+def bf16_activations_enabled() -> bool:
+    return _bf16_activations
+
+
 def set_precision(name: str) -> None:
     """'fp32' (TF32x3 tensor-core mode, fp32-grade) or 'bf16' (bf16 operands, fp32 accumulate)."""
     global _default_precision
@@ -128,8 +141,13 @@ class RGCLayerFn(torch.autograd.Function):
     def forward(ctx, x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var,
                 plan: CsrPlan, cfg: LayerConfig, struct=None):
         _ffi.require_cuda(x, weight, root, nn_w, nn_b)
-        if x.dtype != torch.float32:
-            raise TypeError("node features must be float32 (the arithmetic mode is chosen by `precision`)")
+        # activation storage: fp32 (the API dtype) or, inside a bf16-mode GCN stack, bf16 (see GCN.forward)
+        if x.dtype == torch.bfloat16:
+            if cfg.dtype != _ffi.PB_BF16 or not cfg.batch_norm:
+                raise TypeError("bf16 node features are only taken by BatchNorm-fused layers in the bf16 mode")
+        elif x.dtype != torch.float32:
+            raise TypeError("node features must be float32 (or bfloat16 inside a bf16-mode stack)")
+        act = _ffi.PB_BF16 if x.dtype == torch.bfloat16 else _ffi.PB_F32
         x = x.contiguous()
         n, d = x.shape
         r = plan.n_relations                     # operand blocks per node: R, or 3 slots in the structured layout
@@ -151,12 +169,12 @@ class RGCLayerFn(torch.autograd.Function):
             p = cfg.p_drop if cfg.training else 0.0
             keep_bits = _keep_bits(plan.n_edges, d, p, cfg.seed, dev, st)
             _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
-                  cfg.dtype, _ffi.ptr(keep_bits), p, st)
+                  cfg.dtype, _ffi.ptr(keep_bits), p, act, st)
             ctx.keep_bits = keep_bits
             _, _, wt_hi, wt_lo = _weights(weight, root, n_w, d, cfg.dtype, st)
-            out = torch.empty((n, d), dtype=torch.float32, device=dev)
+            out = torch.empty((n, d), dtype=x.dtype, device=dev)
             _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
-                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, st)
+                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, act, st)
             ctx.operand = (a_hi, a_lo) if cfg.save_operand else None
             ctx.struct = struct
             if not cfg.batch_norm:
@@ -170,12 +188,13 @@ class RGCLayerFn(torch.autograd.Function):
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 _call("pb_bn_stats", out.data_ptr(), d, n, d, groups, gamma.data_ptr(), beta.data_ptr(), cfg.eps,
                       cfg.momentum, _ffi.ptr(running_mean), _ffi.ptr(running_var), save.data_ptr(), coef.data_ptr(),
-                      ws.data_ptr(), ws_bytes, st)
+                      ws.data_ptr(), ws_bytes, act, st)
             else:
                 _call("pb_bn_prepare_eval", gamma.data_ptr(), beta.data_ptr(), running_mean.data_ptr(),
                       running_var.data_ptr(), cfg.eps, d, coef.data_ptr(), st)
-            y = torch.empty((n, d), dtype=torch.float32, device=dev)
-            _call("pb_bn_relu_res_fwd", out.data_ptr(), d, x.data_ptr(), coef.data_ptr(), y.data_ptr(), n, d, groups, 1, st)
+            y = torch.empty((n, d), dtype=x.dtype, device=dev)
+            _call("pb_bn_relu_res_fwd", out.data_ptr(), d, x.data_ptr(), coef.data_ptr(), y.data_ptr(), n, d, groups, 1,
+                  act, st)
         ctx.save_for_backward(x, weight, root, nn_w, nn_b, gamma, out, coef, save)
         ctx.plan, ctx.cfg, ctx.has_bias = plan, cfg, bias is not None
         return y
@@ -186,11 +205,12 @@ class RGCLayerFn(torch.autograd.Function):
         plan: CsrPlan = ctx.plan
         if cfg.batch_norm and not cfg.training:
             raise NotImplementedError("backward through eval-mode BatchNorm is not part of the training path")
-        gy = gy.contiguous()
         if cfg.batch_norm:
             x, weight, root, nn_w, nn_b, gamma, out, coef, save = ctx.saved_tensors
         else:
             x, weight, root, nn_w, nn_b = ctx.saved_tensors
+        act = _ffi.PB_BF16 if x.dtype == torch.bfloat16 else _ffi.PB_F32
+        gy = gy.to(x.dtype).contiguous()             # the gradient travels in the activations' storage dtype
         n, d = x.shape
         r = plan.n_relations
         n_w = weight.shape[0]
@@ -211,7 +231,7 @@ class RGCLayerFn(torch.autograd.Function):
                 g_beta = torch.empty(d, dtype=torch.float32, device=dev)
                 _call("pb_bn_relu_res_bwd", gy.data_ptr(), out.data_ptr(), d, gamma.data_ptr(), save.data_ptr(),
                       coef.data_ptr(), n, d, groups, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d, g_gamma.data_ptr(),
-                      g_beta.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
+                      g_beta.data_ptr(), g_bias.data_ptr(), ws.data_ptr(), ws_bytes, act, st)
             else:
                 _call("pb_grad_prep", gy.data_ptr(), d, n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
                       g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
@@ -223,7 +243,7 @@ class RGCLayerFn(torch.autograd.Function):
             else:  # recompute the aggregated operand instead of keeping N x (R+1)d per layer alive
                 a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
                 _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
-                      cfg.dtype, _ffi.ptr(ctx.keep_bits), p, st)
+                      cfg.dtype, _ffi.ptr(ctx.keep_bits), p, act, st)
             w_hi, w_lo, _, _ = _weights(weight, root, n_w, d, cfg.dtype, st)
             kw = (n_w + 1) * d
             # structured layout: one split-K launch whose splits follow the row groups + a grouped reduce that sums
@@ -237,12 +257,12 @@ class RGCLayerFn(torch.autograd.Function):
             d_a = torch.empty((n, k), dtype=torch.bfloat16 if cfg.dtype == _ffi.PB_BF16 else torch.float32, device=dev)
             _call("pb_rgcn_gemm_bwd_data", g_hi.data_ptr(), _ffi.ptr(g_lo), d, w_hi.data_ptr(), _ffi.ptr(w_lo),
                   d_a.data_ptr(), k, n, d, k, groups, cfg.dtype, st)
-            gx = torch.empty((n, d), dtype=torch.float32, device=dev)
+            gx = torch.empty((n, d), dtype=x.dtype, device=dev)
             q_buf = torch.empty((max(plan.n_edges, 1), d), dtype=d_a.dtype, device=dev)
             partials = torch.empty((plan.n_dist_items, d), dtype=torch.float32, device=dev)
             _call("pb_agg_bwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
                   gy.data_ptr() if cfg.batch_norm else None, gx.data_ptr(), q_buf.data_ptr(), partials.data_ptr(),
-                  _ffi.ptr(ctx.keep_bits), p, st)
+                  _ffi.ptr(ctx.keep_bits), p, act, st)
             g_nn_w = torch.empty((d, _ffi.N_DISTS), dtype=torch.float32, device=dev)
             g_nn_b = torch.empty(d, dtype=torch.float32, device=dev)
             _call("pb_edge_table_bwd", partials.data_ptr(), plan.dist_item_ptr.data_ptr(), d, g_nn_w.data_ptr(),

@@ -73,7 +73,7 @@ def test_gemm_fwd(cuda, dtype_name, m, d):
     w_hi, w_lo = operands(wt, dtype)
     out = torch.full((m, d), float("nan"), device=cuda)
     ffi.check(ffi.lib().pb_rgcn_gemm_fwd(ptr(a_hi), ptr(a_lo), k, ptr(w_hi), ptr(w_lo), ptr(bias), ptr(out), d, m, d, k,
-                                         None, dtype, st()), "pb_rgcn_gemm_fwd")
+                                         None, dtype, ffi.PB_F32, st()), "pb_rgcn_gemm_fwd")
     torch.cuda.synchronize()
     ref = as_f64(a_hi, a_lo) @ as_f64(w_hi, w_lo).t() + bias.double()
     tol = dict(rtol=2e-3, atol=2e-3) if dtype_name == "bf16" else F32_TOL
@@ -198,18 +198,27 @@ def test_agg_fwd(cuda, d, p_drop):
     a_hi, a_lo = torch.empty(n, k, device=cuda), torch.empty(n, k, device=cuda)
     bits = keep_bits(arrays.edge_index.shape[1], d, p_drop, seed, cuda)
     ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_hi), ptr(a_lo), k, ffi.PB_F32, ptr(bits), p_drop,
-                                   st()), "agg_fwd")
+                                   ffi.PB_F32, st()), "agg_fwd")
     torch.testing.assert_close((a_hi.double() + a_lo.double()).cpu(), ref, rtol=2e-6, atol=1e-6)
     assert ((a_hi.view(torch.int32) & 8191) == 0).all()          # hi is a clean TF32 value
     a_bf = torch.empty(n, k, dtype=torch.bfloat16, device=cuda)
     ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a_bf), None, k, ffi.PB_BF16, ptr(bits), p_drop,
-                                   st()), "agg_fwd")
+                                   ffi.PB_F32, st()), "agg_fwd")
     torch.testing.assert_close(a_bf.float().cpu(), ref.float(), rtol=8e-3, atol=1e-6)
+    # bf16 activation storage: the same kernel reading bf16 node features == the fp32 kernel on the rounded features
+    x_bf = xd.to(torch.bfloat16)
+    a_bf2, a_bf3 = torch.empty_like(a_bf), torch.empty_like(a_bf)
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(x_bf), d, ptr(table), ptr(a_bf2), None, k, ffi.PB_BF16, ptr(bits), p_drop,
+                                   ffi.PB_BF16, st()), "agg_fwd")
+    x_rounded = x_bf.float()
+    ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(x_rounded), d, ptr(table), ptr(a_bf3), None, k, ffi.PB_BF16, ptr(bits),
+                                   p_drop, ffi.PB_F32, st()), "agg_fwd")
+    assert torch.equal(a_bf2, a_bf3)
     # bit-reproducible
     a2 = torch.empty_like(a_hi)
     l2 = torch.empty_like(a_lo)
     ffi.check(ffi.lib().pb_agg_fwd(g.plan.ref(), ptr(xd), d, ptr(table), ptr(a2), ptr(l2), k, ffi.PB_F32, ptr(bits), p_drop,
-                                   st()), "agg_fwd")
+                                   ffi.PB_F32, st()), "agg_fwd")
     assert torch.equal(a2, a_hi) and torch.equal(l2, a_lo)
 
 
@@ -241,8 +250,19 @@ def test_agg_bwd(cuda, d, p_drop):
         q_buf = torch.empty(n_edges, d, dtype=da_dev.dtype, device=cuda)
         parts = torch.empty(n_items, d, device=cuda)
         ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gx),
-                                       ptr(q_buf), ptr(parts), ptr(bits), p_drop, st()), "agg_bwd")
+                                       ptr(q_buf), ptr(parts), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd")
         torch.testing.assert_close(gx.double().cpu(), gx_ref, **tol)
+        if dtype == ffi.PB_BF16:
+            # bf16 activation storage == the fp32-storage kernel on the rounded inputs, output rounded to bf16
+            xb, gyb = x_dev.to(torch.bfloat16), gy_dev.to(torch.bfloat16)
+            gxb, partsb = torch.empty(n, d, dtype=torch.bfloat16, device=cuda), torch.empty_like(parts)
+            ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(xb), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gyb), ptr(gxb),
+                                           ptr(q_buf), ptr(partsb), ptr(bits), p_drop, ffi.PB_BF16, st()), "agg_bwd")
+            xr, gyr = xb.float(), gyb.float()
+            gxr, partsr = torch.empty_like(gx), torch.empty_like(parts)
+            ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(xr), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gyr), ptr(gxr),
+                                           ptr(q_buf), ptr(partsr), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd")
+            assert torch.equal(gxb, gxr.to(torch.bfloat16)) and torch.equal(partsb, partsr)
         g_w, g_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
         ffi.check(ffi.lib().pb_edge_table_bwd(ptr(parts), ptr(g.plan.dist_item_ptr), d, ptr(g_w), ptr(g_b), st()), "table_bwd")
         scale = float(table.grad.abs().max())
@@ -251,7 +271,7 @@ def test_agg_bwd(cuda, d, p_drop):
         if dtype == ffi.PB_F32:
             gx2, parts2 = torch.empty_like(gx), torch.empty_like(parts)
             ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev),
-                                           ptr(gx2), ptr(q_buf), ptr(parts2), ptr(bits), p_drop, st()), "agg_bwd")
+                                           ptr(gx2), ptr(q_buf), ptr(parts2), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd")
             assert torch.equal(gx, gx2) and torch.equal(parts, parts2)
 
 
@@ -276,9 +296,9 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
     coef, save = torch.empty(3, d, device=cuda), torch.empty(2, d, device=cuda)
     ffi.check(lib.pb_bn_stats(ptr(out_d), d, m, d, None, ptr(gamma_d), ptr(beta_d), 1e-5, 0.1, ptr(rm_d), ptr(rv_d),
-                              ptr(save), ptr(coef), ptr(ws), ws_bytes, st()), "bn_stats")
+                              ptr(save), ptr(coef), ptr(ws), ws_bytes, ffi.PB_F32, st()), "bn_stats")
     y = torch.empty(m, d, device=cuda)
-    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef), ptr(y), m, d, None, 1, st()), "bn_fwd")
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef), ptr(y), m, d, None, 1, ffi.PB_F32, st()), "bn_fwd")
     torch.testing.assert_close(y.double().cpu(), y_ref, rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(rm_d.double().cpu(), rm64, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(rv_d.double().cpu(), rv64, rtol=1e-4, atol=1e-5)
@@ -299,7 +319,7 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     g_gamma, g_beta, g_bias = (torch.empty(d, device=cuda) for _ in range(3))
     ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, None, ffi.PB_F32,
                                      ptr(g_hi), ptr(g_lo), d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
-                                     st()), "bn_bwd")
+                                     ffi.PB_F32, st()), "bn_bwd")
     scale = float(g_out_ref.abs().max())
     torch.testing.assert_close((g_hi.double() + g_lo.double()).cpu(), g_out_ref, rtol=1e-4, atol=1e-5 * max(1.0, scale))
     torch.testing.assert_close(g_gamma.double().cpu(), g_gamma_ref, rtol=1e-4, atol=1e-4 * float(g_gamma_ref.abs().max()))
@@ -316,12 +336,32 @@ def test_bn_relu_res_fwd_bwd(cuda, m, d):
     g_bf = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
     ffi.check(lib.pb_bn_relu_res_bwd(ptr(gy_d), ptr(out_d), d, ptr(gamma_d), ptr(save), ptr(coef), m, d, None, ffi.PB_BF16,
                                      ptr(g_bf), None, d, ptr(g_gamma), ptr(g_beta), ptr(g_bias), ptr(ws), ws_bytes,
-                                     st()), "bn_bwd")
+                                     ffi.PB_F32, st()), "bn_bwd")
     torch.testing.assert_close(g_bf.double().cpu(), g_out_ref, rtol=1e-2, atol=1e-2 * max(1.0, scale))
+    # bf16 activation storage: statistics / forward / backward on bf16 `out`, `x`, `gy` == the fp32-storage kernels on
+    # the same (rounded) values; y comes back rounded to bf16
+    out_b, x_b, gy_b = out_d.to(torch.bfloat16), x_d.to(torch.bfloat16), gy_d.to(torch.bfloat16)
+    out_r, x_r, gy_r = out_b.float(), x_b.float(), gy_b.float()
+    res = []
+    for o_t, x_t, g_t, act in ((out_b, x_b, gy_b, ffi.PB_BF16), (out_r, x_r, gy_r, ffi.PB_F32)):
+        rm2, rv2 = dev(rm), dev(rv)
+        coef2, save2 = torch.empty(3, d, device=cuda), torch.empty(2, d, device=cuda)
+        ffi.check(lib.pb_bn_stats(ptr(o_t), d, m, d, None, ptr(gamma_d), ptr(beta_d), 1e-5, 0.1, ptr(rm2), ptr(rv2),
+                                  ptr(save2), ptr(coef2), ptr(ws), ws_bytes, act, st()), "bn_stats")
+        y2 = torch.empty(m, d, dtype=o_t.dtype, device=cuda)
+        ffi.check(lib.pb_bn_relu_res_fwd(ptr(o_t), d, ptr(x_t), ptr(coef2), ptr(y2), m, d, None, 1, act, st()), "bn_fwd")
+        g2 = torch.empty(m, d, dtype=torch.bfloat16, device=cuda)
+        gg2, gb2, gbias2 = (torch.empty(d, device=cuda) for _ in range(3))
+        ffi.check(lib.pb_bn_relu_res_bwd(ptr(g_t), ptr(o_t), d, ptr(gamma_d), ptr(save2), ptr(coef2), m, d, None, ffi.PB_BF16,
+                                         ptr(g2), None, d, ptr(gg2), ptr(gb2), ptr(gbias2), ptr(ws), ws_bytes, act, st()),
+                  "bn_bwd")
+        res.append((coef2, save2, rm2, rv2, y2.to(torch.bfloat16), g2, gg2, gb2))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
     # eval mode coefficients
     coef_e = torch.empty(3, d, device=cuda)
     ffi.check(lib.pb_bn_prepare_eval(ptr(gamma_d), ptr(beta_d), ptr(rm_d), ptr(rv_d), 1e-5, d, ptr(coef_e), st()), "bn_eval")
-    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef_e), ptr(y), m, d, None, 1, st()), "bn_fwd")
+    ffi.check(lib.pb_bn_relu_res_fwd(ptr(out_d), d, ptr(x_d), ptr(coef_e), ptr(y), m, d, None, 1, ffi.PB_F32, st()), "bn_fwd")
     y_eval = x.double() + torch.relu(torch.nn.functional.batch_norm(out.double(), rm_d.double().cpu(), rv_d.double().cpu(),
                                                                     gamma.double(), beta.double(), False, 0.1, 1e-5))
     torch.testing.assert_close(y.double().cpu(), y_eval, rtol=1e-4, atol=2e-5)

@@ -70,7 +70,8 @@ def layer_sweep():
                 summ = _ffi.profiler.summary()
                 st = graph.structured if pb.ops.structured_enabled() and d % 256 == 0 else None
                 rows = bench.kernel_table(summ, n, e, d, iters, precision, PK, 0.1, slots=3 if st else 6,
-                                          n_rows=st.n_padded if st else n)
+                                          n_rows=st.n_padded if st else n,
+                                          act_bytes=2 if (precision == "bf16" and st and pb.ops.bf16_activations_enabled()) else 4)
                 print(json.dumps({"config": "layer", "d": d, "nodes": n, "edges": e, "precision": precision,
                                   "ms_fwd_bwd": ms, "layout": "structured" if st else "generic",
                                   "kernels": [{k: r[k] for k in ("kernel", "bound", "achieved", "unit", "frac", "avg_ms")}
