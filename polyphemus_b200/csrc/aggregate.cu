@@ -63,9 +63,14 @@ __global__ void edge_table_bias_kernel(const float* __restrict__ g_w, int d, flo
 // (chunk = 4 consecutive channels) — i.e. exactly the channels lane l of a warp owns in agg_fwd.
 static inline int keep_words(int d) { return ((d + 511) / 512) * 32; }   // u16 words per edge
 
-template <int G16>
+// The four hashes of a thread share the edge and differ by 32 in the chunk index, so their SplitMix64 inputs
+// seed + GOLDEN * (ctr + 1), ctr = (eid << 32 | chunk), are  base + k * (32 * GOLDEN)  with one base per thread: the
+// counter multiply is done once (and only its 32-bit pieces: GOLDEN * (eid << 32) keeps just the low word of
+// GOLDEN_lo * eid). Same values as common.cuh::dropout_bits — the integer pipe is what bounds this kernel.
+template <int G16, bool EXACT>   // EXACT: d == 512 * G16, every chunk of the word exists
 __global__ void __launch_bounds__(256) dropout_bits_kernel(int64_t n_edges, int d, uint32_t thresh16, uint64_t seed,
                                                            uint16_t* __restrict__ bits) {
+  constexpr uint64_t kGolden = 0x9E3779B97F4A7C15ull;
   const int nchunk = d >> 2;
   const int64_t total = n_edges * G16 * 32;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -73,16 +78,20 @@ __global__ void __launch_bounds__(256) dropout_bits_kernel(int64_t n_edges, int 
     const int64_t q = i >> 5;
     const int jj = G16 == 1 ? 0 : (int)(q & (G16 - 1));
     const uint32_t e = (uint32_t)(G16 == 1 ? q : q / G16);
+    const uint32_t c0 = (uint32_t)(l + 128 * jj);                       // chunk of nibble 0; nibble k is c0 + 32 k
+    // seed + GOLDEN * ((e << 32) + c0 + 1)
+    uint64_t z0 = seed + ((uint64_t)((uint32_t)kGolden * e) << 32) + kGolden * (uint64_t)(c0 + 1u);
     uint32_t w = 0;
 #pragma unroll
     for (int nib = 0; nib < 4; ++nib) {
-      const int c = l + 32 * (4 * jj + nib);
-      if (c < nchunk) {
-        const uint64_t r = dropout_bits(seed, e, (uint32_t)c);
-        w |= ((uint32_t)((r & 0xFFFFu) >= thresh16) | ((uint32_t)(((r >> 16) & 0xFFFFu) >= thresh16) << 1) |
-              ((uint32_t)(((r >> 32) & 0xFFFFu) >= thresh16) << 2) | ((uint32_t)((r >> 48) >= thresh16) << 3))
-             << (4 * nib);
+      if (EXACT || (int)c0 + 32 * nib < nchunk) {
+        const uint64_t r = splitmix64_mix(z0);
+        const uint32_t lo = (uint32_t)r, hi = (uint32_t)(r >> 32);
+        const uint32_t k4 = (uint32_t)((lo & 0xFFFFu) >= thresh16) | ((uint32_t)((lo >> 16) >= thresh16) << 1) |
+                            ((uint32_t)((hi & 0xFFFFu) >= thresh16) << 2) | ((uint32_t)((hi >> 16) >= thresh16) << 3);
+        w |= k4 << (4 * nib);
       }
+      z0 += 32ull * kGolden;
     }
     bits[i] = (uint16_t)w;
   }
@@ -419,12 +428,13 @@ extern "C" int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_
   if (n_edges == 0) return PB_OK;
   const int64_t total = n_edges * keep_words(d);
   const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
-  if (d <= 512)
-    dropout_bits_kernel<1><<<grid, 256, 0, as_stream(stream)>>>(n_edges, d, dropout_thresh(p_drop), seed,
-                                                                reinterpret_cast<uint16_t*>(keep_bits));
-  else
-    dropout_bits_kernel<2><<<grid, 256, 0, as_stream(stream)>>>(n_edges, d, dropout_thresh(p_drop), seed,
-                                                                reinterpret_cast<uint16_t*>(keep_bits));
+  uint16_t* out = reinterpret_cast<uint16_t*>(keep_bits);
+  const uint32_t th = dropout_thresh(p_drop);
+  cudaStream_t st = as_stream(stream);
+  if (d == 512) dropout_bits_kernel<1, true><<<grid, 256, 0, st>>>(n_edges, d, th, seed, out);
+  else if (d <= 512) dropout_bits_kernel<1, false><<<grid, 256, 0, st>>>(n_edges, d, th, seed, out);
+  else if (d == 1024) dropout_bits_kernel<2, true><<<grid, 256, 0, st>>>(n_edges, d, th, seed, out);
+  else dropout_bits_kernel<2, false><<<grid, 256, 0, st>>>(n_edges, d, th, seed, out);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
