@@ -224,6 +224,41 @@ class ContentEncoder(nn.Module):
             mean, var = bn.running_mean.float(), bn.running_var.float()
         return (table - mean) * torch.rsqrt(var + bn.eps) * bn.weight.float() + bn.bias.float()
 
+    def _bn_tables_batched(self, cnt_p: torch.Tensor, cnt_d: torch.Tensor):
+        """The four training-mode `_bn_table`s of a step in one batched computation (same arithmetic, ~1/3 of the
+        kernel launches): rows 0 / 1 = non-drum / drum pitch tables, rows 2 / 3 = non-drum / drum duration tables
+        (duration rows padded to the pitch vocabulary with zero counts). cnt_p int [2, 131], cnt_d int [2, 99]
+        (index 1 = drum nodes). Running statistics are updated in the reference's order: drum rows before the others,
+        `bn_dur` twice."""
+        bns = (self.bn_non_drums, self.bn_drums, self.bn_dur, self.bn_dur)
+        pad_v = N_PITCH_TOKENS - N_DUR_TOKENS
+        dur_w = F.pad(self.dur_emb.weight.float(), (0, pad_v))                           # [c, 131], zero columns
+        w_all = torch.stack((self.non_drums_pitch_emb.weight.float(), self.drums_pitch_emb.weight.float(), dur_w, dur_w))
+        b_all = torch.stack((self.non_drums_pitch_emb.bias.float(), self.drums_pitch_emb.bias.float(),
+                             self.dur_emb.bias.float(), self.dur_emb.bias.float()))
+        table = w_all.transpose(1, 2) + b_all.unsqueeze(1)                               # [4, 131, c]
+        cnt = torch.cat((cnt_p, F.pad(cnt_d, (0, pad_v))), dim=0).to(table.dtype)        # [4, 131]
+        n_true = cnt.sum(1, keepdim=True)                                                # [4, 1]
+        n = n_true.clamp(min=1.0)
+        mean = torch.bmm(cnt.unsqueeze(1), table).squeeze(1) / n                         # [4, c]
+        ctr = table - mean.unsqueeze(1)
+        var = torch.bmm(cnt.unsqueeze(1), ctr.square()).squeeze(1) / n                   # biased, as BatchNorm normalises
+        with torch.no_grad():
+            unbiased = var * (n / (n - 1).clamp(min=1.0))
+            alive = (n_true > 0).to(table.dtype)                                         # empty set: statistics untouched
+            for i in (1, 0, 3, 2):                                                       # drums first; bn_dur: drum, other
+                bn = bns[i]
+                m_eff = alive[i] * bn.momentum
+                bn.running_mean.add_(m_eff * (mean[i] - bn.running_mean))
+                bn.running_var.add_(m_eff * (unbiased[i] - bn.running_var))
+                bn.num_batches_tracked.add_(alive[i, 0].to(bn.num_batches_tracked.dtype))
+        gamma = torch.stack([bn.weight.float() for bn in bns])
+        beta = torch.stack([bn.bias.float() for bn in bns])
+        eps = bns[0].eps if len({bn.eps for bn in bns}) == 1 else torch.tensor(
+            [bn.eps for bn in bns], dtype=table.dtype, device=table.device).view(4, 1)
+        out = ctr * (torch.rsqrt(var + eps) * gamma).unsqueeze(1) + beta.unsqueeze(1)
+        return out[:2], out[2:, :N_DUR_TOKENS]
+
     def _embed_folded(self, tokens: torch.Tensor, is_drum: torch.Tensor) -> torch.Tensor:
         """tokens int16 [N, 16, 2], is_drum bool [N] -> relu'd chord embeddings f32 [N, d] in node order.
 
@@ -242,15 +277,20 @@ class ContentEncoder(nn.Module):
                 cnt_p = torch.bincount((ids[..., 0] + N_PITCH_TOKENS * sets).reshape(-1), minlength=2 * N_PITCH_TOKENS)
                 cnt_d = torch.bincount((ids[..., 1] + N_DUR_TOKENS * sets).reshape(-1), minlength=2 * N_DUR_TOKENS)
                 counts = (cnt_p.view(2, -1), cnt_d.view(2, -1))
-            pick = lambda c, i: None if c is None else c[i]
-            # the reference embeds the drum rows first, then the others (bn_dur's running statistics see both)
-            p_drum = self._bn_table(self.drums_pitch_emb, self.bn_drums, None, self.training, pick(counts[0], 1))
-            d_drum = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 1))
-            p_other = self._bn_table(self.non_drums_pitch_emb, self.bn_non_drums, None, self.training, pick(counts[0], 0))
-            d_other = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 0))
+            if self.training and all(bn.track_running_stats and bn.momentum is not None
+                                     for bn in (self.bn_drums, self.bn_non_drums, self.bn_dur)):
+                p_tabs, d_tabs = self._bn_tables_batched(*counts)                  # [2, 131, c], [2, 99, c]
+            else:
+                pick = lambda c, i: None if c is None else c[i]
+                # the reference embeds the drum rows first, then the others (bn_dur's running statistics see both)
+                p_drum = self._bn_table(self.drums_pitch_emb, self.bn_drums, None, self.training, pick(counts[0], 1))
+                d_drum = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 1))
+                p_other = self._bn_table(self.non_drums_pitch_emb, self.bn_non_drums, None, self.training, pick(counts[0], 0))
+                d_other = self._bn_table(self.dur_emb, self.bn_dur, None, self.training, pick(counts[1], 0))
+                p_tabs, d_tabs = torch.stack((p_other, p_drum)), torch.stack((d_other, d_drum))
             w = self.chord_encoder.weight.float().view(d, t, 2, half)             # [out, slot, pitch|dur, half]
-            t_pitch = torch.einsum("svh,oth->stvo", torch.stack((p_other, p_drum)), w[:, :, 0])
-            t_dur = torch.einsum("svh,oth->stvo", torch.stack((d_other, d_drum)), w[:, :, 1])
+            t_pitch = torch.einsum("svh,oth->stvo", p_tabs, w[:, :, 0])
+            t_dur = torch.einsum("svh,oth->stvo", d_tabs, w[:, :, 1])
             tables = torch.cat((t_pitch, t_dur), dim=2)                           # [2, 15, 230, d]
             return ops.chord_embed(tables, self.chord_encoder.bias, tokens, is_drum, tok_offset=2,
                                    dur_off=N_PITCH_TOKENS)
