@@ -4,6 +4,8 @@
            d in {256, 512, 1024}, bf16 and fp32(tf32x3) — per-kernel CUDA-event times vs the HBM / tensor roofline
   batch    LMD16 training step at per-GPU batch 256..2048 (seq/s, peak memory)
   generate LMD2 decoder-only generation of 4096 sequences with structure.json conditioning (and unconditioned)
+  density  LMD16 batch 256 at structure densities 0.1 / 0.25 / 0.5 / 1.0 (graph size, build time, step time)
+  precision LMD16 batch 256 step in the fp32-grade mode next to bf16
 
     python tools/sweep.py layer|batch|generate  > gpurun_out/sweep_<name>.jsonl
 """
@@ -126,5 +128,51 @@ def generate_sweep():
                               "seq_per_s": n / ms * 1e3, "nodes": int(out.shape[0])}), flush=True)
 
 
+def density_sweep():
+    """LMD16 batch 256 at structure densities 0.1 .. 1.0: graph size, device graph build time, bf16 step time."""
+    pb.set_precision("bf16")
+    for p in (0.1, 0.25, 0.5, 1.0):
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        try:
+            host = synthetic_host_batch(256, 16, p, seed=0)
+            build_ms = timed(lambda: device_batch(host, dev), 5)
+            graph = device_batch(host, dev)
+            model = pb.VAE(**bench.MODEL_CFG, device=dev).to(dev).train()
+            step = TrainStep(model, autocast_bf16=True, **bench.ADAM)
+            fn = lambda: step(device_batch(host, dev))
+            for _ in range(3):
+                fn()
+            ms = timed(fn, 5)
+            print(json.dumps({"config": "density", "p": p, "nodes": graph.num_nodes, "edges": graph.num_edges,
+                              "edges_per_node": graph.num_edges / graph.num_nodes, "graph_build_ms": build_ms,
+                              "ms_per_step": ms, "seq_per_s": 256 / ms * 1e3,
+                              "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+            del model, step, graph
+        except torch.OutOfMemoryError as exc:
+            print(json.dumps({"config": "density", "p": p, "error": "out of memory", "detail": str(exc)[:120]}), flush=True)
+
+
+def precision_sweep():
+    """LMD16 batch 256 step in the fp32-grade mode (TF32x3 tensor-core split) next to bf16."""
+    for precision in ("bf16", "fp32"):
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        pb.set_precision(precision)
+        torch.manual_seed(0)
+        model = pb.VAE(**bench.MODEL_CFG, device=dev).to(dev).train()
+        step = TrainStep(model, autocast_bf16=precision == "bf16", **bench.ADAM)
+        host = synthetic_host_batch(256, 16, 0.25, seed=0)
+        fn = lambda: step(device_batch(host, dev))
+        for _ in range(3):
+            fn()
+        ms = timed(fn, 5)
+        print(json.dumps({"config": "precision", "precision": precision, "ms_per_step": ms, "seq_per_s": 256 / ms * 1e3,
+                          "peak_mem_gib": torch.cuda.max_memory_allocated() / 2**30}), flush=True)
+        del model, step
+    pb.set_precision("bf16")
+
+
 if __name__ == "__main__":
-    {"layer": layer_sweep, "batch": batch_sweep, "generate": generate_sweep}[sys.argv[1]]()
+    {"layer": layer_sweep, "batch": batch_sweep, "generate": generate_sweep, "density": density_sweep,
+     "precision": precision_sweep}[sys.argv[1]]()
