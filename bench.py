@@ -333,7 +333,7 @@ def main():
                         "algorithmic_per_launch": top["algorithmic_per_launch"],
                         "share_of_step": top["ms_per_step"] / (total_ms / args.steps)}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only (the other ranks would wait)
             v, times = time_cpu_baseline(args.cpu_batch, MODEL_CFG["n_bars"], 2, 1)
             cpu = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
                    "sample": f"oracle port (reference algorithm, PyTorch CPU fp32), LMD16 batch {args.cpu_batch}: graph build + "
