@@ -133,9 +133,26 @@ class EventProfiler:
     def __init__(self):
         self.records = []       # (name, start_event, end_event, meta)
         self.enabled = False
+        self._pool = []         # timing events are reused across resets: creating them costs more than recording them
+        self._used = 0
 
     def reset(self):
         self.records = []
+        self._used = 0
+
+    def reserve(self, n_calls: int) -> None:
+        """Create the events of `n_calls` bracketed calls ahead of a timed region."""
+        need = self._used + 2 * n_calls - len(self._pool)
+        if need > 0:
+            self._pool.extend(torch.cuda.Event(enable_timing=True) for _ in range(need))
+
+    def events(self):
+        """Two timing events from the pool (grown on demand)."""
+        if self._used + 2 > len(self._pool):
+            self._pool.extend(torch.cuda.Event(enable_timing=True) for _ in range(1024))
+        e0, e1 = self._pool[self._used], self._pool[self._used + 1]
+        self._used += 2
+        return e0, e1
 
     def summary(self):
         """{name: {"calls": n, "ms": total_ms, "meta": last meta}} — call after torch.cuda.synchronize()."""
@@ -155,7 +172,7 @@ def call(name: str, *args, tag=None) -> None:
     the path, so that they are not counted as message-passing launches)."""
     fn = getattr(lib(), name)
     if profiler.enabled:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1 = profiler.events()
         e0.record()
         rc = fn(*args)
         e1.record()
