@@ -206,3 +206,51 @@ def test_grad_all_reducer_world_size_2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 2
+
+
+def test_batched_bn_tables_match_per_table_path():
+    """ContentEncoder._bn_tables_batched (one batched computation for the four BatchNorm(Linear(one_hot)) tables of a
+    step) == four `_bn_table` calls in the reference's order: tables, gradients and running statistics, including a
+    token set that is empty (no drum nodes)."""
+    import copy
+
+    import polyphemus_b200 as pb
+    from polyphemus_b200.vae import N_DUR_TOKENS, N_PITCH_TOKENS
+
+    torch.manual_seed(0)
+    cfg = dict(dropout=0, batch_norm=True, gnn_n_layers=1, d=64, n_bars=2, resolution=8)
+    enc_a = pb.ContentEncoder(**cfg).train()
+    with torch.no_grad():
+        for p in enc_a.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    enc_b = copy.deepcopy(enc_a)
+    gen = torch.Generator().manual_seed(1)
+    for empty_drums in (False, True):
+        cnt_p = torch.randint(0, 50, (2, N_PITCH_TOKENS), generator=gen)
+        cnt_d = torch.randint(0, 50, (2, N_DUR_TOKENS), generator=gen)
+        if empty_drums:
+            cnt_p[1], cnt_d[1] = 0, 0
+        p_tabs, d_tabs = enc_a._bn_tables_batched(cnt_p, cnt_d)
+        ref_p1 = enc_b._bn_table(enc_b.drums_pitch_emb, enc_b.bn_drums, None, True, cnt_p[1])
+        ref_d1 = enc_b._bn_table(enc_b.dur_emb, enc_b.bn_dur, None, True, cnt_d[1])
+        ref_p0 = enc_b._bn_table(enc_b.non_drums_pitch_emb, enc_b.bn_non_drums, None, True, cnt_p[0])
+        ref_d0 = enc_b._bn_table(enc_b.dur_emb, enc_b.bn_dur, None, True, cnt_d[0])
+        for got, want in ((p_tabs[0], ref_p0), (p_tabs[1], ref_p1), (d_tabs[0], ref_d0), (d_tabs[1], ref_d1)):
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-5)
+        w = torch.randn(2, N_PITCH_TOKENS, 32, generator=gen), torch.randn(2, N_DUR_TOKENS, 32, generator=gen)
+        ((p_tabs * w[0]).sum() + (d_tabs * w[1]).sum()).backward()
+        ((torch.stack((ref_p0, ref_p1)) * w[0]).sum() + (torch.stack((ref_d0, ref_d1)) * w[1]).sum()).backward()
+    for (name, pa), (_, pb_) in zip(enc_a.named_parameters(), enc_b.named_parameters()):
+        if pa.grad is None:
+            assert pb_.grad is None, name
+            continue
+        # (a bias in front of a BatchNorm has a mathematically zero gradient whenever its token set is not empty: both
+        # sides then hold round-off only, hence the absolute tolerance at the scale of the weight gradient)
+        ref_w = dict(enc_b.named_parameters()).get(name.replace(".bias", ".weight"))
+        scale = float(pb_.grad.abs().max()) if ref_w is None or ref_w.grad is None else float(ref_w.grad.abs().max())
+        torch.testing.assert_close(pa.grad, pb_.grad, rtol=1e-4, atol=1e-5 * max(scale, 1e-30), msg=name)
+    sa, sb = enc_a.state_dict(), enc_b.state_dict()
+    for k in sa:
+        if "running" in k or "num_batches" in k:
+            torch.testing.assert_close(sa[k].float(), sb[k].float(), rtol=1e-5, atol=1e-6, msg=k)
