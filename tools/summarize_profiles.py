@@ -84,6 +84,7 @@ def traffic_json():
         "pb_agg_bwd": ("aggbwd", ["agg_bwd_dx_kernel"]),
         "pb_dist_reduce": ("distred", ["dist_reduce_kernel"]),
         "pb_rgcn_gemm_fwd": ("gemm", ["gemm_tcgen05_kernel"]),
+        "pb::gemm_tcgen05_kernel": ("gemm", ["gemm_tcgen05_kernel"]),     # mean of the captured launches
         "pb_bn_relu_res_fwd": ("bn", ["bn_apply_kernel"]),
         "pb_bn_stats": ("bn", ["bn_stats_partial_kernel", "bn_stats_finalize_kernel"]),
     }
