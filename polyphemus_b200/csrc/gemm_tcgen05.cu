@@ -6,11 +6,12 @@
 //   bwd-data  dA[M,K]   = g[M,d] . Wcat^T                (A K-major,  B = Wcat   K-major)
 //   bwd-wt    dWcat[K,d]= A^T . g  (split over nodes)    (A MN-major, B MN-major — no transposed copies)
 //
-// Structure (one CTA per SM, 192 threads):
+// Structure (one CTA per SM; 192 threads, 320 in the bf16 kernel):
 //   warp 0    TMA producer: cp.async.bulk.tensor (128B swizzle) into a multi-stage smem ring, mbarrier tx
 //   warp 1    MMA issuer: one lane issues tcgen05.mma (A,B from smem descriptors, D in TMEM, fp32 accumulate),
 //             tcgen05.commit releases smem stages and publishes the accumulator
 //   warps 2-5 epilogue: tcgen05.ld the accumulator (one TMEM lane quadrant per warp), bias / convert, store
+//   warps 6-9 (bf16 kernel, bf16 output): second epilogue group, the two groups split the tile's columns
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 //
 // Precision modes: PB_BF16 -> kind::f16 (bf16 operands), 1 MMA per k-step, tile 128x256x64;
@@ -150,13 +151,19 @@ struct Cfg {
   // epilogue staging: per epilogue warp one 32-row x 32-column chunk, rows padded by 16 B (conflict-free both ways)
   static constexpr int kStageRowF32 = 144, kStageRowBf16 = 80;
   static constexpr int kEpiStageBytes = 32 * kStageRowF32;     // per warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4 * kEpiStageBytes;
+  // warps 2-5 own full-size staging slots (fp32 or bf16 rows); warps 6-9 only ever stage bf16 rows
+  static constexpr int kEpiStageBytesBf16 = 32 * kStageRowBf16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 4 * kEpiStageBytes +
+                                    4 * kEpiStageBytesBf16;
 };
 
-constexpr int kGemmThreads = 192;
+// warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 second epilogue group (bf16 output of the bf16 kernel only:
+// the two groups split the tile's columns — a short-K GEMM such as the data gradient (8 k-blocks per tile) is bound
+// by how fast the accumulator leaves TMEM, not by the tensor pipe)
+template <bool BF16> constexpr int kGemmThreads = BF16 ? 320 : 192;   // the tf32 kernel keeps its register budget
 
 template <bool BF16>
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BF16>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -172,7 +179,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < C::kSplit; ++s) { tma_prefetch_desc(&p.tm_a[s]); tma_prefetch_desc(&p.tm_b[s]); }
     for (int s = 0; s < C::kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, 4); }
+    const uint32_t n_epi = (BF16 && p.out_bf16) ? 8 : 4;
+    for (int b = 0; b < 2; ++b) { mbar_init(tmem_full + b, 1); mbar_init(tmem_empty + b, n_epi); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -279,15 +287,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         }
       }
     }
-  } else {
-    // ================================================================== epilogue (warps 2..5)
+  } else if (warp < 6 || (BF16 && p.out_bf16)) {
+    // ================================================================== epilogue (warps 2..5, and 6..9 for bf16 output)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    const bool split_cols = BF16 && p.out_bf16;            // two warps per quadrant, half of the columns each
+    const int col_lo = split_cols ? ((warp - 2) >> 2) * (C::BN / 2) : 0;
+    const int col_hi = split_cols ? col_lo + C::BN / 2 : C::BN;
     int buf = 0;
     uint32_t buf_phase = 0;
     // One 32-row x 32-column chunk of the tile (thread = row after tcgen05.ld): bias / convert into a padded smem
     // staging buffer of this warp, then store with lanes running along the row — every global store instruction
     // writes whole 64/128-byte row segments instead of 32 scattered 16-byte pieces.
-    uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 + (warp - 2) * C::kEpiStageBytes;
+    uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 +
+                     (warp < 6 ? (warp - 2) * C::kEpiStageBytes : 4 * C::kEpiStageBytes + (warp - 6) * C::kEpiStageBytesBf16);
     auto store_chunk = [&](const float* v, int64_t row0, int col, int split) {
       if (p.out_bf16) {
         uint8_t* mine = stage + lane * C::kStageRowBf16;
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tcgen05_kernel(const __g
         mbar_wait(tmem_full + buf, buf_phase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::BN; c0 += 32) {
+        for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
           uint32_t v[32];
           tmem_ld_32x32(lane_base + (uint32_t)(buf * C::BN + c0), v);
           if (row0 < p.m && n0 + c0 < p.n)   // warp-uniform; n is a multiple of 32 (host check): whole chunk in range
@@ -593,7 +605,7 @@ static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n,
     PB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_set = true;
   }
-  gemm_tcgen05_kernel<BF16><<<grid, kGemmThreads, C::kSmemBytes, st>>>(p);
+  gemm_tcgen05_kernel<BF16><<<grid, kGemmThreads<BF16>, C::kSmemBytes, st>>>(p);
   PB_LAUNCH_CHECK();
   return p.num_splits;  // > 0
 }
