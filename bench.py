@@ -251,16 +251,31 @@ def main():
     hosts = [synthetic_host_batch(args.batch, MODEL_CFG["n_bars"], DENSITY, seed=1000 * rank + i) for i in range(n_variants)]
     resident = [(h.s_tensor.to(dev), h.tokens.to(dev)) for h in hosts]
 
-    def step_resident(i):
+    # Every step builds its graph on the device; the build of step i+1 is issued on a side stream before step i is
+    # enqueued (train.BatchPrefetcher), as a data loader would, so its size read-back does not drain the training stream.
+    from polyphemus_b200.train import BatchPrefetcher, HostBatch
+    prefetch = BatchPrefetcher(dev)
+    pending = {"resident": None, "e2e": None}
+    loss_host = torch.empty(max(args.steps, args.warmup, 2) + 1, dtype=torch.float32).pin_memory()
+
+    def resident_batch(i):
         s_dev, tok = resident[i % n_variants]
-        from polyphemus_b200.train import HostBatch
-        graph = device_batch(HostBatch(s_dev.clone(), tok), dev)
+        return lambda: HostBatch(s_dev.clone(), tok)               # the builder writes fake activations in place
+
+    def step_resident(i):
+        if pending["resident"] is None:
+            pending["resident"] = prefetch.submit(resident_batch(i))
+        graph = prefetch.take(pending["resident"])
+        pending["resident"] = prefetch.submit(resident_batch(i + 1))
         return step_fn(graph)
 
     def step_e2e(i):
-        graph = device_batch(hosts[i % n_variants], dev)            # pinned host -> device inside the timed region
+        if pending["e2e"] is None:
+            pending["e2e"] = prefetch.submit(hosts[i % n_variants])
+        graph = prefetch.take(pending["e2e"])
+        pending["e2e"] = prefetch.submit(hosts[(i + 1) % n_variants])   # pinned host -> device inside the timed region
         loss, _ = step_fn(graph)
-        return float(loss)                                          # D2H read of the step's result
+        loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)  # D2H read of the step's result (read after the region)
 
     def barrier():
         if world > 1:

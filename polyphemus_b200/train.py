@@ -150,6 +150,39 @@ def device_batch(host: HostBatch, device, onehot: bool = False, onehot_dtype=tor
     return graph
 
 
+class BatchPrefetcher:
+    """Builds the next batch's device graph on a side CUDA stream while the current step runs.
+
+    `device_batch` ends its counting pass with the one host read-back that sizes the graph. On the training stream that
+    read-back waits for everything queued before it — the whole previous step — so the host can never run ahead of
+    the device and every host-bound stretch of a step shows up as device idle time. On a side stream it only waits
+    for the (sub-millisecond) counting kernels; the reference overlaps graph construction with training the same way,
+    through DataLoader worker processes (train.py:152-156). `take()` makes the training stream wait for the build and
+    hands the tensors' memory over to it."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+
+    def submit(self, host, **kw):
+        """`host`: a HostBatch, or a callable returning one (run under the side stream — e.g. a clone of tensors that
+        are already resident). Its tensors must not depend on work still queued on the training stream."""
+        with torch.cuda.stream(self.stream):
+            graph = device_batch(host() if callable(host) else host, self.device, **kw)
+            ready = torch.cuda.Event()
+            ready.record()
+        return graph, ready
+
+    def take(self, pending) -> Graph:
+        graph, ready = pending
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(ready)
+        for v in vars(graph).values():             # allocated on the side stream, consumed (and freed) on this one
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                v.record_stream(main)
+        return graph
+
+
 # ------------------------------------------------------------------------------------------ data parallel
 class GradAllReducer:
     """Flat-buffer gradient all-reduce (sum then 1/world) overlapped with backward.
