@@ -13,7 +13,7 @@ from . import _ffi
 from ._ffi import PolyphemusB200Error
 from .conv import GCL, GCN, BatchNorm
 from .graph import CsrPlan, Graph, decode_edge_attrs, graph_from_tensor, graphs_from_tensor
-from .ops import get_precision, launch_counter, set_precision
+from .ops import get_precision, launch_counter, set_bf16_activations, set_precision
 from .vae import VAE, ContentDecoder, ContentEncoder, Decoder, Encoder, StructureDecoder, StructureEncoder
 
 __version__ = "0.1.0"
@@ -21,5 +21,5 @@ __version__ = "0.1.0"
 __all__ = [
     "GCL", "GCN", "BatchNorm", "VAE", "Encoder", "Decoder", "ContentEncoder", "ContentDecoder", "StructureEncoder",
     "StructureDecoder", "Graph", "CsrPlan", "graph_from_tensor", "graphs_from_tensor", "decode_edge_attrs",
-    "set_precision", "get_precision", "launch_counter", "PolyphemusB200Error",
+    "set_precision", "get_precision", "set_bf16_activations", "launch_counter", "PolyphemusB200Error",
 ]
