@@ -66,6 +66,7 @@ class GCL(nn.Module):
         self.precision = precision
         self.reset_edge_nn()
         self._plan_key = None
+        self._plan_src = None
         self._plan = None
 
     def reset_parameters(self) -> None:
@@ -85,12 +86,16 @@ class GCL(nn.Module):
         return lin.weight, lin.bias
 
     def plan_from(self, x, edge_index, edge_type, edge_attr) -> CsrPlan:
-        key = (edge_index.data_ptr(), tuple(edge_index.shape), edge_type.data_ptr(), edge_attr.data_ptr(),
-               edge_index._version, edge_attr._version, int(x.size(0)))
-        if key != self._plan_key:
+        """CSR plan of a foreign (PyG-style) edge list. The last plan is reused only for the *same tensor objects* at
+        the same in-place version: the cache holds references to them, so the caching allocator cannot hand their
+        addresses to a different graph while the entry is alive (the reference rebuilds its masks on every call)."""
+        src = (edge_index, edge_type, edge_attr)
+        key = (edge_index._version, edge_type._version, edge_attr._version, tuple(edge_index.shape), int(x.size(0)))
+        cached = self._plan_src
+        if cached is None or key != self._plan_key or any(a is not b for a, b in zip(cached, src)):
             t8, d8 = decode_edge_attrs(edge_type, edge_attr)
             self._plan = CsrPlan(edge_index, t8, d8, int(x.size(0)), self.num_relations)
-            self._plan_key = key
+            self._plan_key, self._plan_src = key, src
         return self._plan
 
     def forward(self, x, edge_index=None, edge_type=None, edge_attr=None, *, plan: Optional[CsrPlan] = None,

@@ -600,10 +600,13 @@ static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n,
   }
   const int64_t total = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_splits;
   const int grid = (int)std::min<int64_t>(total, sm_count());
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the dynamic shared-memory limit is a per-device function attribute: set it once on every device that launches
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     PB_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   gemm_tcgen05_kernel<BF16><<<grid, kGemmThreads<BF16>, C::kSmemBytes, st>>>(p);
   PB_LAUNCH_CHECK();

@@ -134,8 +134,14 @@ class Graph:
 
     @edge_attrs.setter
     def edge_attrs(self, value):
+        """Replacing the edge attributes replaces the graph's relations / distances: everything derived from them
+        (uint8 type / distance, the CSR plans, the structured layout — only valid for builder graphs) is dropped."""
         self._edge_attrs = value
         self._plan = None
+        self._structured = None
+        if value is not None and "edge_type" in self.__dict__:
+            self.edge_type, self.edge_dist = decode_edge_attrs(value[:, 0], value[:, 1:])
+            self.group_counts = None          # no longer known to be a builder graph
 
     @property
     def plan(self) -> CsrPlan:

@@ -185,24 +185,27 @@ class BatchPrefetcher:
 
 # ------------------------------------------------------------------------------------------ data parallel
 class GradAllReducer:
-    """Flat-buffer gradient all-reduce (sum then 1/world) overlapped with backward.
+    """Flat-buffer gradient all-reduce (NCCL average) overlapped with backward.
 
     Parameters are bucketed in reverse registration order (the order backward produces them) over one contiguous
     fp32 buffer. Backward leaves every gradient where autograd puts it (no per-parameter accumulation kernels); a
-    post-accumulate hook counts ready parameters, and the moment a bucket is complete its gradients are packed into
-    the buffer with ONE multi-tensor copy and ``all_reduce`` is launched on that slice. ``finish()`` flushes the
-    buckets of parameters that never receive a gradient (the 12 ``decoder.s_decoder.*`` tensors, whose loss term is
-    constant — training.py:307 — keep a zero slot, identically on every rank), waits, averages, and points every
-    ``.grad`` at its slice of the buffer for the optimizer.
+    post-accumulate hook counts ready parameters, and the moment bucket b is complete AND buckets 0..b-1 have been
+    launched, its gradients are packed into the buffer with ONE multi-tensor copy and ``all_reduce(AVG)`` is launched on
+    that slice — strictly in bucket order, so every rank issues the identical collective sequence even when a rank is
+    missing a gradient (e.g. a shard without drum nodes). ``finish()`` flushes the remaining buckets (parameters that
+    never receive a gradient — the 12 ``decoder.s_decoder.*`` tensors, whose loss term is constant, training.py:307 —
+    keep a zero slot, identically on every rank), waits, and points every ``.grad`` at its slice of the buffer for
+    the optimizer. The buckets produced last are small (``tail_mb``) so that the exposed tail after backward is short.
     """
 
-    def __init__(self, params, bucket_mb: float = 32.0, process_group=None):
+    def __init__(self, params, bucket_mb: float = 32.0, process_group=None, tail_mb: float = 4.0):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         dev = self.params[0].device
         self.sync = True             # False: no exchange (single-rank checks); finish() still packs the buffer
         self.flat = None
+        self._hook_handles = []
         if self.world == 1:          # nothing to exchange: plain per-parameter gradients, dropped between steps
             return
         total = sum(p.numel() for p in self.params)
@@ -211,6 +214,7 @@ class GradAllReducer:
         self._bucket_of = {}
         self._view = {}
         limit = int(bucket_mb * (1 << 20) / 4)
+        tail = min(int(tail_mb * (1 << 20) / 4), limit)
         off, start, members = 0, 0, []
         for p in reversed(self.params):
             n = p.numel()
@@ -218,16 +222,26 @@ class GradAllReducer:
             self._bucket_of[p] = len(self.buckets)
             members.append(p)
             off += n
-            if off - start >= limit:
+            # the last `2 * tail` elements of the buffer (the gradients backward produces last) go in small buckets
+            cap = tail if total - off < 2 * tail else limit
+            if off - start >= cap:
                 self.buckets.append((start, off, members))
                 start, members = off, []
         if members:
             self.buckets.append((start, off, members))
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
+        self._next = 0
         self._handles = []
+        self._avg = dist.ReduceOp.AVG if dist.get_backend(process_group) == "nccl" else None
         for p in self.params:
-            p.register_post_accumulate_grad_hook(self._hook)
+            self._hook_handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def close(self) -> None:
+        """Remove the autograd hooks (a second reducer on the same parameters must not double-count)."""
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles = []
 
     def _pack(self, b: int) -> None:
         """Gradients of bucket b -> their slices of the flat buffer (one multi-tensor copy; missing ones stay zero)."""
@@ -242,15 +256,24 @@ class GradAllReducer:
         self._pack(b)
         if self.sync:
             s, e, _ = self.buckets[b]
-            self._handles.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            if self._avg is not None:
+                op = self._avg
+            else:                                # gloo has no AVG: pre-scale, then sum
+                self.flat[s:e].mul_(1.0 / self.world)
+                op = dist.ReduceOp.SUM
+            self._handles.append(dist.all_reduce(self.flat[s:e], op=op, group=self.group, async_op=True))
+
+    def _advance(self) -> None:
+        """Launch complete buckets strictly in index order."""
+        while self._next < len(self.buckets) and self._ready[self._next] >= len(self.buckets[self._next][2]):
+            self._launch(self._next)
+            self._next += 1
 
     def _hook(self, p) -> None:
         if not self.sync:
             return
-        b = self._bucket_of[p]
-        self._ready[b] += 1
-        if self._ready[b] == len(self.buckets[b][2]):
-            self._launch(b)
+        self._ready[self._bucket_of[p]] += 1
+        self._advance()
 
     def zero_grad(self) -> None:
         for p in self.params:
@@ -260,24 +283,44 @@ class GradAllReducer:
         self.flat.zero_()
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
+        self._next = 0
 
     def finish(self) -> None:
-        """Flush incomplete buckets, wait for all reductions, average, expose the buffer slices as ``.grad``."""
+        """Flush incomplete buckets in order, wait for all reductions, expose the buffer slices as ``.grad``."""
         if self.flat is None:
             return
         for b in range(len(self.buckets)):
             self._launch(b)
+        self._next = len(self.buckets)
         for h in self._handles:
             h.wait()
         self._handles = []
-        if self.sync:
-            self.flat.mul_(1.0 / self.world)
         for p in self.params:
             p.grad = self._view[p]
 
+    def sync_buffers(self, model) -> None:
+        """Average the floating-point buffers (BatchNorm running statistics are per replica during training) across
+        ranks, e.g. before a checkpoint is written from rank 0."""
+        if self.world == 1:
+            return
+        bufs = [b for b in model.buffers() if b.is_floating_point()]
+        if not bufs:
+            return
+        flat = torch.cat([b.reshape(-1).float() for b in bufs])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+        flat.div_(self.world)
+        off = 0
+        for b in bufs:
+            b.copy_(flat[off:off + b.numel()].view_as(b))
+            off += b.numel()
+
 
 class TrainStep:
-    """graph build -> forward -> loss -> backward -> gradient all-reduce -> Adam (train.py:176-207 config)."""
+    """graph build -> forward -> loss -> backward -> gradient all-reduce -> Adam (train.py:176-207 config).
+
+    While a TrainStep is alive the content decoder returns the head outputs (``LogitParts``) instead of assembling the
+    dense ``[N, 15, 230]`` logits — the step only needs the loss; ``close()`` restores the reference behaviour of
+    ``model(graph)`` and removes the gradient hooks."""
 
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.98), eps: float = 1e-9, autocast_bf16: bool = False,
                  beta_kld: float = 0.0, bucket_mb: float = 32.0):
@@ -286,9 +329,22 @@ class TrainStep:
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, fused=model_is_cuda(model))
         self.autocast_bf16 = autocast_bf16
         self.beta_kld = beta_kld
-        for m in model.modules():            # the step only needs the loss: keep the content logits as head outputs
-            if hasattr(m, "materialize_logits"):
-                m.materialize_logits = False
+        self._lazy = [(m, m.materialize_logits) for m in model.modules() if hasattr(m, "materialize_logits")]
+        for m, _ in self._lazy:
+            m.materialize_logits = False
+
+    def close(self) -> None:
+        for m, was in self._lazy:
+            m.materialize_logits = was
+        self._lazy = []
+        self.reducer.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def __call__(self, graph: Graph, noise: Optional[torch.Tensor] = None):
         self.reducer.zero_grad()
