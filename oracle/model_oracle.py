@@ -45,6 +45,8 @@ class Ctx:
     training: bool = True
     gcl_dropout: float = 0.0
     gcl_keep_masks: Optional[dict] = None      # {(gcn_prefix, layer): bool/float [E, d] keep-mask}
+    gcl_random_dropout: bool = False           # no mask given: draw the GCL dropout with F.dropout (as model.py:133)
+    emulate_bf16: bool = False                 # round where the bf16 mode of the CUDA path rounds (see _rb)
     running: dict = field(default_factory=dict)
 
 
@@ -65,10 +67,20 @@ def _bn(sd, prefix, x, ctx: Ctx):
     return y
 
 
+def _rb(t: Tensor) -> Tensor:
+    """Round to bf16 and back (straight-through gradient). NOT part of the reference: it places the roundings of the
+    CUDA path's bf16 mode (GEMM operands [H_r | x] and weights in bf16, fp32 accumulation, the
+    pre-BatchNorm output and the layer output stored in bf16) into the reference's arithmetic, so that a bf16-mode
+    result can be checked to rounding level — against the fp32 arithmetic the two differ by ReLU decisions that bf16
+    round-off flips, which says nothing about the implementation."""
+    return t + (t.to(torch.bfloat16).to(t.dtype) - t).detach()
+
+
 # ----------------------------------------------------------------------------- message passing
 def gcl_forward(x: Tensor, edge_index: Tensor, edge_type: Tensor, edge_dist: Tensor,
                 weight: Tensor, root: Tensor, bias: Tensor, nn_w: Tensor, nn_b: Tensor,
-                keep_mask: Optional[Tensor] = None, p_drop: float = 0.0) -> Tensor:
+                keep_mask: Optional[Tensor] = None, p_drop: float = 0.0, random_dropout: bool = False,
+                emulate_bf16: bool = False) -> Tensor:
     """One relational graph-conv layer. edge_dist = argmax of the one-hot edge_attr (model.py:194).
 
     out[v] = sum_r mean_{e: dst=v, type=r} dropout(relu(x[src_e] * (A[:, dist_e] + a))) @ W_r + x[v] @ root + bias
@@ -83,10 +95,17 @@ def gcl_forward(x: Tensor, edge_index: Tensor, edge_type: Tensor, edge_dist: Ten
         msg = F.relu(x.index_select(0, src) * gate)            # model.py:131-132
         if keep_mask is not None and p_drop > 0:
             msg = msg * keep_mask[sel].to(x.dtype) / (1.0 - p_drop)   # model.py:133
+        elif random_dropout and p_drop > 0:
+            msg = F.dropout(msg, p=p_drop, training=True)      # model.py:133 as shipped
         agg = torch.zeros(n, d_in, dtype=x.dtype).index_add_(0, dst, msg)
         cnt = torch.zeros(n, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.shape[0], dtype=x.dtype))
         agg = agg / cnt.clamp(min=1).unsqueeze(1)              # scatter-mean
-        out = out + agg @ weight[r]                            # model.py:112
+        if emulate_bf16:
+            out = out + _rb(agg) @ _rb(weight[r])
+        else:
+            out = out + agg @ weight[r]                        # model.py:112
+    if emulate_bf16:
+        return _rb(out + _rb(x) @ _rb(root) + bias)
     out = out + x @ root                                       # model.py:116
     return out + bias                                          # model.py:119
 
@@ -96,15 +115,20 @@ def gcn_forward(sd, prefix: str, x: Tensor, edge_index: Tensor, edge_type: Tenso
     """The GCL stack with BatchNorm/ReLU/residual (model.py:196-206). Config dropout is 0."""
     if n_layers is None:
         n_layers = 1 + max(int(k[len(prefix) + 8:].split(".")[0]) for k in sd if k.startswith(prefix + ".layers."))
+    if ctx.emulate_bf16:
+        x = _rb(x)
     for i in range(n_layers):
         lp = f"{prefix}.layers.{i}"
         keep = None if ctx.gcl_keep_masks is None else ctx.gcl_keep_masks.get((prefix, i))
         h = gcl_forward(x, edge_index, edge_type, edge_dist, sd[lp + ".weight"], sd[lp + ".root"],
                         sd[lp + ".bias"], sd[lp + ".nn.weight"], sd[lp + ".nn.bias"],
-                        keep_mask=keep if ctx.training else None, p_drop=ctx.gcl_dropout)
+                        keep_mask=keep if ctx.training else None, p_drop=ctx.gcl_dropout if ctx.training else 0.0,
+                        random_dropout=ctx.gcl_random_dropout and ctx.training, emulate_bf16=ctx.emulate_bf16)
         if f"{prefix}.norm_layers.{i}.module.weight" in sd:
             h = _bn(sd, f"{prefix}.norm_layers.{i}.module", h, ctx)
         x = x + F.relu(h)
+        if ctx.emulate_bf16:
+            x = _rb(x)
     return x
 
 
