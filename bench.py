@@ -166,6 +166,9 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
     algo = {
         "pb_agg_fwd": ("hbm", n * d * ab + eb * e + 4 * (n * r + 1) + 128 * d + n * k * s),
         "pb_agg_bwd": ("hbm", n * k * s_da + 2 * n * d * ab + 16 * e + 4 * (n + 1) + n * d * ab + 128 * d + parts),
+        # the fused backward moves the same compulsory data (its work list is 16 B per edge + 48 B per node instead of
+        # 16 B per edge + 4 B per node; the denominator is kept identical to round 1's for comparability)
+        "pb_agg_bwd_fused": ("hbm", n * k * s_da + 2 * n * d * ab + 16 * e + 4 * (n + 1) + n * d * ab + 128 * d + parts),
         "pb_bn_stats": ("hbm", n * d * ab),
         "pb_bn_relu_res_fwd": ("hbm", 3 * n * d * ab),
         "pb_bn_relu_res_bwd": ("hbm", 4 * n * d * ab + n * d * s),

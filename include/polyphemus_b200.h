@@ -135,10 +135,21 @@ typedef struct pb_csr {
    * track relation but visits them bar by bar, so that a bar's rows (spread over the four groups) are gathered
    * while they are still in L2. */
   const int32_t* node_order;
+  /* int4 [n_nodes] = {row, first out-edge, out-degree, first in-edge} per visited node, in visiting order
+   * (pb_csr_visit_meta, after node_order is set): the fused backward reads it 32 sources per coalesced load instead
+   * of chasing node_order -> out_ptr per source. */
+  const void* visit_meta;
+  /* the fused backward's work list (pb_csr_bwd_stream): int4 [3 n_nodes + n_edges] records in visiting order, per
+   * source {x row, root-block row, residual row, out-edge rows...}; visit_edge_ptr i32 [n_nodes + 1] = exclusive sum of
+   * the out-degrees in visiting order (record position of source i = 3 i + visit_edge_ptr[i]). */
+  const void* bwd_stream;
+  const int32_t* visit_edge_ptr;
 } pb_csr_t;
 
 size_t pb_csr_workspace_bytes(int64_t n_nodes, int64_t n_edges, int32_t n_relations);
 int32_t pb_csr_num_dist_items(void);
+int pb_csr_visit_meta(const pb_csr_t* csr, void* visit_meta /* int4 [n_nodes] */, pb_stream_t stream);
+int pb_csr_bwd_stream(const pb_csr_t* csr, const int32_t* visit_edge_ptr, void* bwd_stream, pb_stream_t stream);
 int pb_csr_build(const int64_t* edge_index, const uint8_t* edge_type, const uint8_t* edge_dist,
                  int64_t n_nodes, int64_t n_edges, int32_t n_relations, int32_t* in_ptr, int32_t* in_edge,
                  int32_t* in_eid, int32_t* out_ptr, void* out_rec, int32_t* dist_perm, void* dist_items,
@@ -184,6 +195,17 @@ int pb_agg_fwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table
 int pb_agg_bwd(const pb_csr_t* csr, const void* x, int32_t d, const float* table, const void* d_a,
                int64_t ldda, int32_t dtype, const void* gy_res, void* gx, void* q_buf, float* dtable_partials,
                const void* keep_bits, float p_drop, int32_t act_dtype, pb_stream_t stream);
+/* Fused backward (the product path): the same gx and edge-table gradient WITHOUT the q_buf round trip. A CTA owns a
+ * contiguous range of sources and its threads own channel columns — of the gathered rows, of gx, and of a [32, d] fp32
+ * accumulator in shared memory, so the 32-bin reduction dT[dist_e] += ds_e * x[src_e] needs neither atomics nor
+ * barriers and adds in edge order (bit-reproducible). dtable_partials is f32 [pb_agg_bwd_num_partials(n, d), 32, d]
+ * (one block per CTA), finished by pb_edge_table_bwd_fused. Needs csr->bwd_stream; d_a must be packed (ldda == (R+1) d). */
+int32_t pb_agg_bwd_num_partials(int64_t n_nodes, int32_t d, int32_t dtype);
+int pb_agg_bwd_fused(const pb_csr_t* csr, const void* x, int32_t d, const float* table, const void* d_a,
+                     int64_t ldda, int32_t dtype, const void* gy_res, void* gx, float* dtable_partials,
+                     const void* keep_bits, float p_drop, int32_t act_dtype, pb_stream_t stream);
+int pb_edge_table_bwd_fused(const float* dtable_partials, int32_t n_partials, int32_t d, float* g_nn_weight,
+                            float* g_nn_bias, pb_stream_t stream);
 int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep /*[E,d]*/,
                     pb_stream_t stream);
 

@@ -12,7 +12,8 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int6
 import torch
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libpolyphemus_b200.so")
+# PB200_LIB: load another build of the same library (A/B measurements of kernel variants)
+LIB_PATH = os.environ.get("PB200_LIB") or os.path.join(_PKG_DIR, "lib", "libpolyphemus_b200.so")
 
 PB_F32 = 0
 PB_BF16 = 1
@@ -29,7 +30,7 @@ class CsrStruct(Structure):
         ("n_nodes", c_int64), ("n_edges", c_int64), ("n_relations", c_int32), ("reserved", c_int32),
         ("in_ptr", c_void_p), ("in_edge", c_void_p), ("in_eid", c_void_p), ("out_ptr", c_void_p),
         ("out_rec", c_void_p), ("dist_perm", c_void_p), ("dist_items", c_void_p), ("dist_item_ptr", c_void_p),
-        ("node_order", c_void_p),
+        ("node_order", c_void_p), ("visit_meta", c_void_p), ("bwd_stream", c_void_p), ("visit_edge_ptr", c_void_p),
     ]
 
 
@@ -59,6 +60,11 @@ SIGNATURES = {
     "pb_agg_bwd": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, _P, c_float, c_int32,
                            _P]),
     "pb_dropout_mask": (c_int, [c_int64, c_int32, c_float, c_uint64, _P, _P]),
+    "pb_csr_visit_meta": (c_int, [POINTER(CsrStruct), _P, _P]),
+    "pb_csr_bwd_stream": (c_int, [POINTER(CsrStruct), _P, _P, _P]),
+    "pb_agg_bwd_num_partials": (c_int32, [c_int64, c_int32, c_int32]),
+    "pb_agg_bwd_fused": (c_int, [POINTER(CsrStruct), _P, c_int32, _P, _P, c_int64, c_int32, _P, _P, _P, _P, c_float, c_int32, _P]),
+    "pb_edge_table_bwd_fused": (c_int, [_P, c_int32, c_int32, _P, _P, _P]),
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
                                  POINTER(GroupsStruct), c_int32, c_int32, _P]),
@@ -118,7 +124,7 @@ def lib() -> ctypes.CDLL:
 # host-only queries are not counted).
 LAUNCHES = {
     "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
-    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
+    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_edge_table_bwd_fused": 2, "pb_agg_bwd_fused": 1, "pb_csr_visit_meta": 1, "pb_csr_bwd_stream": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_ce_rows_fwd": 1, "pb_ce_rows_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,

@@ -9,6 +9,8 @@
 // 32-row table lookup T[dist] (pb_edge_table_fwd).
 //
 // The kernel writes the tensor-core operand A = [H_0 | ... | H_{R-1} | x] directly in the GEMM's dtype.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pb {
@@ -385,6 +387,263 @@ __global__ void __launch_bounds__(kQThreads) dist_reduce_kernel(const void* __re
   }
 }
 
+// ---------------------------------------------------------------------------------------------- fused backward
+// Scatter-by-source AND the edge-table gradient in one pass, no E x d intermediate (the legacy path above writes the
+// rows q_e = ds_e * x[src_e] to HBM and reads them back grouped by distance: 2 x E x d bytes of pure overhead).
+//
+// The obstacle is the 32-bin reduction dT[dist_e] += q_e. Here a CTA owns a contiguous range of source nodes (in
+// visiting order) and its threads split the CHANNELS: thread t owns channels [t*CH, t*CH + CH) of every row the CTA
+// touches — of the gradient rows it gathers, of gx, and of a [32, d] fp32 accumulator dT in shared memory. Nobody
+// else ever touches those columns, so the accumulation needs no atomics, no barriers and no inter-warp ordering: the
+// warps of a CTA run completely independently (each is a channel slice of the same source stream), and the order of
+// additions into every accumulator word is the order of the edges — bit-reproducible. Consecutive edges with the
+// same distance (the ONSET edges of a source all have distance 0, its NEXT edges share one distance) are summed in
+// registers first. Every CTA leaves its [32, d] partial in `partials`; pb_edge_table_bwd_fused adds them in fixed
+// order.
+//
+// Latency hiding: a warp sees only d / n_warps channels of a row (256 B of a 1 KB bf16 row), so it must keep many
+// rows in flight. The work of a source range is therefore laid out by the plan as ONE flat record stream
+// (pb_csr_bwd_stream): per source {x row, root-block row, residual row, out-edge rows...}, one 16-byte record each.
+// A warp loads 32 records per coalesced load (two chunks ahead) and keeps a ring of kRing rows in flight in
+// registers: slot s of the ring is consumed (record p) and immediately refilled with the row of record p + kRing.
+// The ring is indexed statically (the trip over its slots is fully unrolled), so nothing is spilled or rotated.
+constexpr int kRing = 16;
+enum : int { kRecEdge = 0, kRecX = 1, kRecRoot = 2, kRecRes = 3, kRecNop = 4, kRecLast = 8 };
+
+template <int W> struct RawW { uint32_t w[W]; };
+template <int W>
+__device__ __forceinline__ RawW<W> ld_raw(const void* p) {   // read-once data: keep it out of L1 (the edge table lives there)
+  RawW<W> r;
+  if constexpr (W == 1) {
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r.w[0]) : "l"(p));
+  } else if constexpr (W == 2) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.w[0]), "=r"(r.w[1]) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3])
+                 : "l"(p));
+  }
+  return r;
+}
+// CH values stored as bf16 (BF) or fp32 in the first CH * (BF ? 2 : 4) / 4 words
+template <bool BF, int CH, int W>
+__device__ __forceinline__ void unpack_raw(const RawW<W>& r, float v[CH]) {
+  if constexpr (BF) {
+#pragma unroll
+    for (int i = 0; i < CH / 2; ++i) { const float2 f = unpack_bf16x2(r.w[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r.w[i]);
+  }
+}
+template <bool BF, int CH, int W>
+__device__ __forceinline__ RawW<W> ld_vals(const void* base, size_t elem) {
+  constexpr int N = CH * (BF ? 2 : 4) / 4;
+  const RawW<N> t = ld_raw<N>(static_cast<const char*>(base) + elem * (BF ? 2 : 4));
+  RawW<W> r;
+#pragma unroll
+  for (int i = 0; i < W; ++i) r.w[i] = i < N ? t.w[i < N ? i : 0] : 0u;
+  return r;
+}
+template <bool BF, int CH>
+__device__ __forceinline__ void store_vals(void* base, size_t elem, const float v[CH]) {
+  if constexpr (BF) {
+    if constexpr (CH == 4) st_stream2(static_cast<__nv_bfloat16*>(base) + elem, make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3])));
+    else {
+      const uint32_t u = pack_bf16x2(v[0], v[1]);
+      asm volatile("st.global.L1::no_allocate.b32 [%0], %1;" ::"l"(static_cast<__nv_bfloat16*>(base) + elem), "r"(u) : "memory");
+    }
+  } else {
+    if constexpr (CH == 4) st_stream4(static_cast<float*>(base) + elem, make_float4(v[0], v[1], v[2], v[3]));
+    else asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(static_cast<float*>(base) + elem), "f"(v[0]), "f"(v[1]) : "memory");
+  }
+}
+
+template <bool BF16, bool DROPOUT, int CH, bool ABF>
+__global__ void __launch_bounds__(256) agg_bwd_fused_kernel(
+    const int4* __restrict__ stream, const int* __restrict__ visit_edge_ptr, const void* __restrict__ x,
+    const float* __restrict__ table, const void* __restrict__ d_a, const void* __restrict__ gy_res,
+    void* __restrict__ gx, float* __restrict__ partials, int64_t n_nodes, int d,
+    const uint16_t* __restrict__ keep_bits, float keep_scale) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int GW = CH * (BF16 ? 2 : 4) / 4, XW = CH * (ABF ? 2 : 4) / 4, W = GW > XW ? GW : XW;
+  extern __shared__ float dT_s[];                        // [32][d]; column c belongs to thread c / CH
+  const int lane = threadIdx.x & 31;
+  const int c0 = threadIdx.x * CH;                       // blockDim.x * CH == d
+  const int g16 = (d + 511) / 512;                       // keep-bit words per edge / 32
+  const int cidx = c0 >> 2;                              // 4-channel chunk of the keep-bit layout
+  const int kb_word = (cidx >> 7) * 32 + (cidx & 31), kb_shift = 4 * ((cidx >> 5) & 3) + (CH == 2 ? (c0 & 2) : 0);
+  float* my_t = dT_s + c0;
+#pragma unroll 4
+  for (int k = 0; k < PB_N_DISTS; ++k)
+#pragma unroll
+    for (int j = 0; j < CH; ++j) my_t[k * d + j] = 0.f;
+
+  const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = r0 + per < n_nodes ? r0 + per : n_nodes;
+
+  if (r0 < r1) {
+    const int64_t p0 = 3 * r0 + __ldg(visit_edge_ptr + r0), p1 = 3 * r1 + __ldg(visit_edge_ptr + r1);
+    auto load_recs = [&](int64_t base) {
+      return base + lane < p1 ? __ldg(stream + base + lane) : make_int4(0, kRecNop, 0, 0);
+    };
+    // state of the source being consumed
+    float xu[CH], acc[CH], run_q[CH];
+    int run_dist = 0, cur_u = 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) { xu[j] = 0.f; acc[j] = 0.f; run_q[j] = 0.f; }
+    auto flush_run = [&]() {
+      float* p = my_t + run_dist * d;
+      if constexpr (CH == 4) {
+        float4 v = *reinterpret_cast<float4*>(p);
+        v.x += run_q[0]; v.y += run_q[1]; v.z += run_q[2]; v.w += run_q[3];
+        *reinterpret_cast<float4*>(p) = v;
+      } else {
+        float2 v = *reinterpret_cast<float2*>(p);
+        v.x += run_q[0]; v.y += run_q[1];
+        *reinterpret_cast<float2*>(p) = v;
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) run_q[j] = 0.f;
+    };
+    RawW<W> ring[kRing];
+    uint32_t ring_kb[kRing];
+    // issue the row of record (rx, ry, rz) into ring slot s
+    auto issue = [&](RawW<W>& slot, uint32_t& kb, int rx, int ry, int rz) {
+      const int kind = ry & 7;
+      const size_t off = (size_t)(uint32_t)rx * d + c0;
+      if (kind == kRecEdge || kind == kRecRoot) {                 // warp-uniform
+        slot = ld_vals<BF16, CH, W>(d_a, off);
+        if constexpr (DROPOUT)
+          if (kind == kRecEdge) kb = __ldg(keep_bits + (size_t)(uint32_t)rz * g16 * 32 + kb_word);
+      } else if (kind == kRecX) {
+        slot = ld_vals<ABF, CH, W>(x, off);
+      } else if (kind == kRecRes) {
+        if (gy_res) slot = ld_vals<ABF, CH, W>(gy_res, off);
+      }
+    };
+    auto consume = [&](const RawW<W>& slot, uint32_t kb, int ry, int rz, int rw) {
+      const int kind = ry & 7;
+      float v[CH];
+      if (kind == kRecEdge) {
+        const int dist = (ry >> 8) & (PB_N_DISTS - 1);
+        float t[CH];
+        if constexpr (CH == 4) { const float4 tv = ldg4(table + (size_t)dist * d + c0); t[0] = tv.x; t[1] = tv.y; t[2] = tv.z; t[3] = tv.w; }
+        else { const float2 tv = __ldg(reinterpret_cast<const float2*>(table + (size_t)dist * d + c0)); t[0] = tv.x; t[1] = tv.y; }
+        unpack_raw<BF16, CH, W>(slot, v);
+        float coef = __int_as_float(rw);                          // 1 / |segment|, from the plan
+        if constexpr (DROPOUT) coef *= keep_scale;
+        if (dist != run_dist) { flush_run(); run_dist = dist; }   // warp-uniform
+        const uint32_t bits = DROPOUT ? (kb >> kb_shift) : 0xFu;
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          const bool keep = ((bits >> j) & 1u) && xu[j] * t[j] > 0.f;
+          const float ds = keep ? v[j] * coef : 0.f;
+          acc[j] += ds * t[j];
+          run_q[j] += ds * xu[j];
+        }
+      } else if (kind == kRecX) {
+        unpack_raw<ABF, CH, W>(slot, xu);
+        cur_u = rz;                                               // header records carry the source row in z
+      } else if (kind == kRecRoot) {
+        unpack_raw<BF16, CH, W>(slot, acc);
+      } else if (kind == kRecRes) {
+        if (gy_res) {
+          unpack_raw<ABF, CH, W>(slot, v);
+#pragma unroll
+          for (int j = 0; j < CH; ++j) acc[j] += v[j];
+        }
+      }
+      if (ry & kRecLast) store_vals<ABF, CH>(gx, (size_t)(uint32_t)cur_u * d + c0, acc);
+    };
+
+    int4 recs_cur = load_recs(p0), recs_nxt = load_recs(p0 + 32);
+#pragma unroll
+    for (int s = 0; s < kRing; ++s)
+      issue(ring[s], ring_kb[s], __shfl_sync(kFull, recs_cur.x, s), __shfl_sync(kFull, recs_cur.y, s),
+            __shfl_sync(kFull, recs_cur.z, s));
+    for (int64_t base = p0; base < p1; base += 32) {
+      const int4 recs_nn = load_recs(base + 64);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        // records base + 16 half + s are in the ring; refill with records base + 16 half + 16 + s
+        const int4 nx = half ? recs_nxt : recs_cur;
+        const int lc = 16 * half, ln = 16 - 16 * half;
+#pragma unroll
+        for (int s = 0; s < kRing; ++s) {
+          consume(ring[s], ring_kb[s], __shfl_sync(kFull, recs_cur.y, lc + s), __shfl_sync(kFull, recs_cur.z, lc + s),
+                  __shfl_sync(kFull, recs_cur.w, lc + s));
+          issue(ring[s], ring_kb[s], __shfl_sync(kFull, nx.x, ln + s), __shfl_sync(kFull, nx.y, ln + s),
+                __shfl_sync(kFull, nx.z, ln + s));
+        }
+      }
+      recs_cur = recs_nxt;
+      recs_nxt = recs_nn;
+    }
+    flush_run();
+  }
+  __syncwarp();
+  float* out = partials + (size_t)blockIdx.x * PB_N_DISTS * d + c0;
+#pragma unroll 4
+  for (int k = 0; k < PB_N_DISTS; ++k)
+#pragma unroll
+    for (int j = 0; j < CH; ++j) out[(size_t)k * d + j] = my_t[k * d + j];
+}
+
+// The record stream of the fused backward, in visiting order: per source {X, ROOT, RES, out-edges...}.
+//   x = row-block index: the row u for X / RES (rows of x / gy_res), u * (R+1) + R for ROOT and dst * (R+1) + slot for
+//       an edge (blocks of d elements inside d_a [n, (R+1) d])
+//   y = kind | kRecLast on the source's last record | dist << 8      z = edge id (edge) / row u (header records)
+//   w = 1 / |segment(dst, slot)| as float bits (edge)
+__global__ void bwd_stream_kernel(const int4* __restrict__ visit_meta, const int* __restrict__ visit_edge_ptr,
+                                  const int4* __restrict__ out_rec, int n_rel, int64_t n_nodes, int4* __restrict__ stream) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int4 m = visit_meta[i];                         // {row, first out-edge, out-degree, -}
+  int4* o = stream + 3 * i + visit_edge_ptr[i];
+  const int u = m.x, deg = m.z;
+  o[0] = make_int4(u, kRecX, u, 0);
+  o[1] = make_int4(u * (n_rel + 1) + n_rel, kRecRoot, u, 0);
+  o[2] = make_int4(u, kRecRes | (deg == 0 ? kRecLast : 0), u, 0);
+  for (int s = 0; s < deg; ++s) {
+    const int4 r = out_rec[m.y + s];                     // {dst, slot | dist << 8, eid, |segment|}
+    const float coef = r.w > 1 ? 1.0f / (float)r.w : 1.0f;
+    o[3 + s] = make_int4(r.x * (n_rel + 1) + (r.y & 0xff), kRecEdge | (s == deg - 1 ? kRecLast : 0) | (r.y & 0x1f00), r.z,
+                         __float_as_int(coef));
+  }
+}
+
+// partials [P][32][d] (one block per CTA of agg_bwd_fused_kernel) -> g_w [d][32]: grid (d/32, 32 distances), block =
+// 32 channels x 8 lanes over P, lanes combined in fixed order.
+__global__ void __launch_bounds__(256) edge_table_bwd_fused_kernel(const float* __restrict__ partials, int n_part, int d,
+                                                                   float* __restrict__ g_w) {
+  __shared__ float red[8][33];
+  const int ci = threadIdx.x, j = threadIdx.y, k = blockIdx.y;
+  const int c = blockIdx.x * 32 + ci;
+  float s = 0.f;
+  if (c < d)
+    for (int p = j; p < n_part; p += 8) s += partials[((size_t)p * PB_N_DISTS + k) * d + c];
+  red[j][ci] = s;
+  __syncthreads();
+  if (j == 0 && c < d) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][ci];
+    g_w[(size_t)c * PB_N_DISTS + k] = t;
+  }
+}
+
+// {row, first out-edge, out-degree, first in-edge} per visited node, in visiting order
+__global__ void visit_meta_kernel(const int* __restrict__ node_order, const int* __restrict__ out_ptr,
+                                  const int* __restrict__ in_ptr, int n_rel, int64_t n_nodes, int4* __restrict__ meta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int u = node_order ? node_order[i] : (int)i;
+  const int beg = out_ptr[u];
+  meta[i] = make_int4(u, beg, out_ptr[u + 1] - beg, in_ptr[(size_t)u * n_rel]);
+}
+
 static int check_csr(const pb_csr_t* g, int d, const char* who) {
   PB_REQUIRE(g && g->in_ptr && g->in_edge && g->out_ptr && g->out_rec, "%s: incomplete CSR plan", who);
   PB_REQUIRE(g->n_nodes > 0 && g->n_relations > 0 && g->n_relations < 32, "%s: empty graph / too many relations", who);
@@ -557,6 +816,117 @@ extern "C" int pb_agg_bwd(const pb_csr_t* csr, const void* x, int32_t d, const f
   if (dtype == PB_BF16) return bits ? PB_AGG_BWD_CALL(true, true, false) : PB_AGG_BWD_CALL(true, false, false);
   return bits ? PB_AGG_BWD_CALL(false, true, false) : PB_AGG_BWD_CALL(false, false, false);
 #undef PB_AGG_BWD_CALL
+}
+
+// ---- fused backward: launch geometry shared by the kernel launch and the partials-size query
+static int fused_ch(int d) { return d % 128 == 0 ? 4 : 2; }
+static int fused_ctas(int64_t n_nodes, int d) {
+  const size_t smem = (size_t)PB_N_DISTS * d * sizeof(float);
+  int per_sm = (int)((size_t)227 * 1024 / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, 8));
+  const int64_t want = (n_nodes + 63) / 64;                      // at least 64 sources per CTA
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * per_sm));
+}
+
+// PB200_AGG_BWD_TC=0 keeps the CUDA-core variant for eligible shapes too (A/B measurements)
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PB200_AGG_BWD_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+extern "C" int32_t pb_agg_bwd_num_partials(int64_t n_nodes, int32_t d, int32_t dtype) {
+  if (n_nodes <= 0 || d <= 0) return 0;
+  if (tc_enabled() && agg_bwd_tc_eligible(d, dtype)) return agg_bwd_tc_ctas(n_nodes);
+  return fused_ctas(n_nodes, d);
+}
+
+template <bool BF16, bool DROP, int CH, bool ABF>
+static int launch_agg_bwd_fused(const pb_csr_t* g, const void* x, int d, const float* table, const void* d_a,
+                                const void* gy_res, void* gx, float* partials, const uint16_t* bits, float scale,
+                                cudaStream_t st) {
+  const size_t smem = (size_t)PB_N_DISTS * d * sizeof(float);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PB_CUDA(cudaFuncSetAttribute(agg_bwd_fused_kernel<BF16, DROP, CH, ABF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 PB_N_DISTS * 1024 * (int)sizeof(float)));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const int grid = fused_ctas(g->n_nodes, d);
+  agg_bwd_fused_kernel<BF16, DROP, CH, ABF><<<grid, d / CH, smem, st>>>(
+      reinterpret_cast<const int4*>(g->bwd_stream), g->visit_edge_ptr, x, table, d_a, gy_res, gx, partials, g->n_nodes, d,
+      bits, scale);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_agg_bwd_fused(const pb_csr_t* csr, const void* x, int32_t d, const float* table, const void* d_a,
+                                int64_t ldda, int32_t dtype, const void* gy_res, void* gx, float* dtable_partials,
+                                const void* keep_bits, float p_drop, int32_t act_dtype, pb_stream_t stream) {
+  int rc = check_csr(csr, d, "pb_agg_bwd_fused");
+  if (rc) return rc;
+  if ((rc = check_act_dtype(dtype, act_dtype, "pb_agg_bwd_fused"))) return rc;
+  PB_REQUIRE(x && table && d_a && gx && dtable_partials, "pb_agg_bwd_fused: null pointer");
+  PB_REQUIRE(csr->bwd_stream && csr->visit_edge_ptr, "pb_agg_bwd_fused: CSR plan lacks the record stream (pb_csr_bwd_stream)");
+  PB_REQUIRE(ldda == (int64_t)(csr->n_relations + 1) * d, "pb_agg_bwd_fused: d_a must be packed (ldda == (R+1) d)");
+  PB_REQUIRE((int64_t)csr->n_nodes * (csr->n_relations + 1) < ((int64_t)1 << 32), "pb_agg_bwd_fused: too many row blocks");
+  PB_REQUIRE(dtype == PB_BF16 || dtype == PB_F32, "pb_agg_bwd_fused: bad dtype");
+  PB_REQUIRE(ldda >= (int64_t)(csr->n_relations + 1) * d && ldda % 8 == 0, "pb_agg_bwd_fused: bad ldda");
+  PB_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "pb_agg_bwd_fused: p_drop out of range");
+  PB_REQUIRE(p_drop == 0.f || keep_bits, "pb_agg_bwd_fused: p_drop > 0 needs keep_bits (pb_dropout_bits)");
+  cudaStream_t st = as_stream(stream);
+  const uint16_t* bits = p_drop > 0.f ? reinterpret_cast<const uint16_t*>(keep_bits) : nullptr;
+  const float scale = 1.f / (1.f - p_drop);
+  if (tc_enabled() && agg_bwd_tc_eligible(d, dtype)) {
+    PB_REQUIRE(csr->visit_meta, "pb_agg_bwd_fused: CSR plan lacks visit_meta (pb_csr_visit_meta)");
+    return agg_bwd_tc_launch(csr, x, d, table, d_a, ldda, gy_res, gx, dtable_partials, bits, scale, act_dtype == PB_BF16, st);
+  }
+#define PB_FUSED(BF, DR, CH, AB) \
+  launch_agg_bwd_fused<BF, DR, CH, AB>(csr, x, d, table, d_a, gy_res, gx, dtable_partials, bits, scale, st)
+#define PB_FUSED_CH(BF, DR, AB) (fused_ch(d) == 4 ? PB_FUSED(BF, DR, 4, AB) : PB_FUSED(BF, DR, 2, AB))
+  if (dtype == PB_BF16 && act_dtype == PB_BF16) return bits ? PB_FUSED_CH(true, true, true) : PB_FUSED_CH(true, false, true);
+  if (dtype == PB_BF16) return bits ? PB_FUSED_CH(true, true, false) : PB_FUSED_CH(true, false, false);
+  return bits ? PB_FUSED_CH(false, true, false) : PB_FUSED_CH(false, false, false);
+#undef PB_FUSED_CH
+#undef PB_FUSED
+}
+
+extern "C" int pb_edge_table_bwd_fused(const float* dtable_partials, int32_t n_partials, int32_t d, float* g_nn_weight,
+                                       float* g_nn_bias, pb_stream_t stream) {
+  PB_REQUIRE(dtable_partials && g_nn_weight && g_nn_bias && d > 0 && n_partials > 0, "pb_edge_table_bwd_fused: bad arguments");
+  edge_table_bwd_fused_kernel<<<dim3((d + 31) / 32, PB_N_DISTS), dim3(32, 8), 0, as_stream(stream)>>>(
+      dtable_partials, n_partials, d, g_nn_weight);
+  PB_LAUNCH_CHECK();
+  edge_table_bias_kernel<<<(d + 127) / 128, 128, 0, as_stream(stream)>>>(g_nn_weight, d, g_nn_bias);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_csr_bwd_stream(const pb_csr_t* csr, const int32_t* visit_edge_ptr, void* bwd_stream, pb_stream_t stream) {
+  PB_REQUIRE(csr && csr->visit_meta && csr->out_rec && visit_edge_ptr && bwd_stream && csr->n_nodes > 0,
+             "pb_csr_bwd_stream: bad arguments (needs visit_meta)");
+  PB_REQUIRE((reinterpret_cast<uintptr_t>(bwd_stream) & 15) == 0, "pb_csr_bwd_stream: stream must be 16B aligned");
+  const int64_t n = csr->n_nodes;
+  bwd_stream_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const int4*>(csr->visit_meta), visit_edge_ptr, reinterpret_cast<const int4*>(csr->out_rec),
+      csr->n_relations, n, reinterpret_cast<int4*>(bwd_stream));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+extern "C" int pb_csr_visit_meta(const pb_csr_t* csr, void* visit_meta, pb_stream_t stream) {
+  PB_REQUIRE(csr && csr->in_ptr && csr->out_ptr && visit_meta && csr->n_nodes > 0, "pb_csr_visit_meta: bad arguments");
+  PB_REQUIRE((reinterpret_cast<uintptr_t>(visit_meta) & 15) == 0, "pb_csr_visit_meta: visit_meta must be 16B aligned");
+  const int64_t n = csr->n_nodes;
+  visit_meta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(
+      csr->node_order, csr->out_ptr, csr->in_ptr, csr->n_relations, n, reinterpret_cast<int4*>(visit_meta));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
 }
 
 extern "C" int pb_dropout_mask(int64_t n_edges, int32_t d, float p_drop, uint64_t seed, uint8_t* keep,

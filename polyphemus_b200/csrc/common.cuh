@@ -38,6 +38,13 @@ int sm_count();  // cached multiprocessor count of the current device
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// tensor-core aggregation backward (agg_bwd_tc.cu), dispatched by pb_agg_bwd_fused
+bool agg_bwd_tc_eligible(int d, int dtype);
+int agg_bwd_tc_ctas(int64_t n_nodes);
+int agg_bwd_tc_launch(const pb_csr_t* g, const void* x, int d, const float* table, const void* d_a, int64_t ldda,
+                      const void* gy_res, void* gx, float* partials, const uint16_t* bits, float scale, bool act_bf16,
+                      cudaStream_t st);
+
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

@@ -57,14 +57,32 @@ class CsrPlan:
         self.struct = _ffi.CsrStruct(n, e, r, 0, self.in_ptr.data_ptr(), self.in_edge.data_ptr(),
                                      self.in_eid.data_ptr(), self.out_ptr.data_ptr(), self.out_rec.data_ptr(),
                                      self.dist_perm.data_ptr(), self.dist_items.data_ptr(),
-                                     self.dist_item_ptr.data_ptr(), None)
+                                     self.dist_item_ptr.data_ptr(), None, None, None, None)
         self.node_order = None
+        self.visit_meta = torch.empty((n, 4), dtype=torch.int32, device=dev)
+        self._build_visit_meta()
+
+    def _build_visit_meta(self) -> None:
+        """Per visited node {row, first out-edge, out-degree, first in-edge} (pb_csr_visit_meta) and the fused
+        backward's flat record stream in visiting order (pb_csr_bwd_stream)."""
+        st = self.struct
+        st.visit_meta = st.bwd_stream = st.visit_edge_ptr = None
+        with torch.cuda.device(self.device):
+            _ffi.call("pb_csr_visit_meta", ctypes.byref(st), self.visit_meta.data_ptr(), _ffi.stream())
+            st.visit_meta = self.visit_meta.data_ptr()
+            self.visit_edge_ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int32, device=self.device)
+            torch.cumsum(self.visit_meta[:, 2], 0, dtype=torch.int32, out=self.visit_edge_ptr[1:])
+            self.bwd_stream = torch.empty((3 * self.n_nodes + self.n_edges, 4), dtype=torch.int32, device=self.device)
+            _ffi.call("pb_csr_bwd_stream", ctypes.byref(st), self.visit_edge_ptr.data_ptr(), self.bwd_stream.data_ptr(),
+                      _ffi.stream())
+        st.bwd_stream, st.visit_edge_ptr = self.bwd_stream.data_ptr(), self.visit_edge_ptr.data_ptr()
 
     def set_node_order(self, order: torch.Tensor) -> None:
         """Visit the rows in `order` (int32 permutation of 0..n_nodes-1) instead of 0..n-1 (see pb_csr_t)."""
         assert order.dtype == torch.int32 and order.numel() == self.n_nodes
         self.node_order = order.contiguous()
         self.struct.node_order = self.node_order.data_ptr()
+        self._build_visit_meta()
 
     def ref(self):
         return ctypes.byref(self.struct)

@@ -50,6 +50,9 @@ def structured_enabled() -> bool:
 
 
 _bf16_activations = os.environ.get("PB200_BF16_ACT", "1") != "0"
+# "fused" (default): scatter-by-source and the edge-table gradient in one pass, shared-memory accumulators with
+# thread-owned columns; "legacy": the round-1 pair of kernels with the E x d intermediate (kept for A/B measurements)
+_agg_bwd_mode = os.environ.get("PB200_AGG_BWD", "fused")
 
 
 def set_bf16_activations(enabled: bool) -> None:
@@ -258,15 +261,22 @@ class RGCLayerFn(torch.autograd.Function):
             _call("pb_rgcn_gemm_bwd_data", g_hi.data_ptr(), _ffi.ptr(g_lo), d, w_hi.data_ptr(), _ffi.ptr(w_lo),
                   d_a.data_ptr(), k, n, d, k, groups, cfg.dtype, st)
             gx = torch.empty((n, d), dtype=x.dtype, device=dev)
-            q_buf = torch.empty((max(plan.n_edges, 1), d), dtype=d_a.dtype, device=dev)
-            partials = torch.empty((plan.n_dist_items, d), dtype=torch.float32, device=dev)
-            _call("pb_agg_bwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
-                  gy.data_ptr() if cfg.batch_norm else None, gx.data_ptr(), q_buf.data_ptr(), partials.data_ptr(),
-                  _ffi.ptr(ctx.keep_bits), p, act, st)
             g_nn_w = torch.empty((d, _ffi.N_DISTS), dtype=torch.float32, device=dev)
             g_nn_b = torch.empty(d, dtype=torch.float32, device=dev)
-            _call("pb_edge_table_bwd", partials.data_ptr(), plan.dist_item_ptr.data_ptr(), d, g_nn_w.data_ptr(),
-                  g_nn_b.data_ptr(), st)
+            gy_res = gy.data_ptr() if cfg.batch_norm else None
+            if _agg_bwd_mode == "fused":
+                n_part = int(lib.pb_agg_bwd_num_partials(n, d, cfg.dtype))
+                partials = torch.empty((n_part, _ffi.N_DISTS, d), dtype=torch.float32, device=dev)
+                _call("pb_agg_bwd_fused", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
+                      gy_res, gx.data_ptr(), partials.data_ptr(), _ffi.ptr(ctx.keep_bits), p, act, st)
+                _call("pb_edge_table_bwd_fused", partials.data_ptr(), n_part, d, g_nn_w.data_ptr(), g_nn_b.data_ptr(), st)
+            else:
+                q_buf = torch.empty((max(plan.n_edges, 1), d), dtype=d_a.dtype, device=dev)
+                partials = torch.empty((plan.n_dist_items, d), dtype=torch.float32, device=dev)
+                _call("pb_agg_bwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), d_a.data_ptr(), k, cfg.dtype,
+                      gy_res, gx.data_ptr(), q_buf.data_ptr(), partials.data_ptr(), _ffi.ptr(ctx.keep_bits), p, act, st)
+                _call("pb_edge_table_bwd", partials.data_ptr(), plan.dist_item_ptr.data_ptr(), d, g_nn_w.data_ptr(),
+                      g_nn_b.data_ptr(), st)
         g_weight = d_wcat[: n_w * d].view(n_w, d, d)
         g_root = d_wcat[n_w * d:]
         return (gx, g_weight, g_root, g_bias if ctx.has_bias else None, g_nn_w, g_nn_b, g_gamma, g_beta,

@@ -273,6 +273,129 @@ def test_agg_bwd(cuda, d, p_drop):
             ffi.check(ffi.lib().pb_agg_bwd(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev),
                                            ptr(gx2), ptr(q_buf), ptr(parts2), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd")
             assert torch.equal(gx, gx2) and torch.equal(parts, parts2)
+        # ---- the fused kernel (product path): same gx bit for bit (same additions in the same order), the table
+        # gradient accumulated without the E x d intermediate
+        n_part = ffi.lib().pb_agg_bwd_num_partials(n, d, dtype)
+        fparts = torch.full((n_part, 32, d), float("nan"), device=cuda)
+        gxf = torch.full((n, d), float("nan"), device=cuda)
+        ffi.check(ffi.lib().pb_agg_bwd_fused(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gxf),
+                                             ptr(fparts), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd_fused")
+        assert torch.equal(gxf, gx)
+        fg_w, fg_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+        ffi.check(ffi.lib().pb_edge_table_bwd_fused(ptr(fparts), n_part, d, ptr(fg_w), ptr(fg_b), st()), "table_bwd_fused")
+        # fp32 accumulation of unrounded rows: tighter than the legacy path's bf16 intermediate
+        ftol = dict(rtol=1e-5, atol=1e-5) if dtype == ffi.PB_F32 else dict(rtol=2e-2, atol=2e-2)
+        torch.testing.assert_close(fg_w.double().cpu(), table.grad.t(), rtol=ftol["rtol"], atol=ftol["atol"] * max(1.0, scale))
+        torch.testing.assert_close(fg_b.double().cpu(), table.grad.sum(0), rtol=ftol["rtol"], atol=ftol["atol"] * 8 * max(1.0, scale))
+        gxf2, fparts2 = torch.empty_like(gxf), torch.empty_like(fparts)
+        ffi.check(ffi.lib().pb_agg_bwd_fused(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gy_dev), ptr(gxf2),
+                                             ptr(fparts2), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd_fused")
+        assert torch.equal(gxf, gxf2) and torch.equal(fparts, fparts2)          # bit-reproducible
+        if dtype == ffi.PB_BF16:
+            xb, gyb = x_dev.to(torch.bfloat16), gy_dev.to(torch.bfloat16)
+            gxb, fpartsb = torch.empty(n, d, dtype=torch.bfloat16, device=cuda), torch.empty_like(fparts)
+            ffi.check(ffi.lib().pb_agg_bwd_fused(g.plan.ref(), ptr(xb), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gyb), ptr(gxb),
+                                                 ptr(fpartsb), ptr(bits), p_drop, ffi.PB_BF16, st()), "agg_bwd_fused")
+            xr, gyr = xb.float(), gyb.float()
+            gxr, fpartsr = torch.empty_like(gxf), torch.empty_like(fparts)
+            ffi.check(ffi.lib().pb_agg_bwd_fused(g.plan.ref(), ptr(xr), d, ptr(t_dev), ptr(da_dev), k, dtype, ptr(gyr), ptr(gxr),
+                                                 ptr(fpartsr), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd_fused")
+            assert torch.equal(gxb, gxr.to(torch.bfloat16)) and torch.equal(fpartsb, fpartsr)
+        # no residual branch (plain GCL without BatchNorm)
+        gxn = torch.empty_like(gxf)
+        ffi.check(ffi.lib().pb_agg_bwd_fused(g.plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, dtype, None, ptr(gxn),
+                                             ptr(fparts2), ptr(bits), p_drop, ffi.PB_F32, st()), "agg_bwd_fused")
+        torch.testing.assert_close(gxn.double().cpu(), gx_ref - gy, **tol)
+
+
+@pytest.mark.parametrize("d", [256, 512])
+def test_agg_bwd_tensor_core_large_graph_matches_legacy(cuda, d):
+    """The tensor-core backward (bf16 mode, d in {256, 512}) on a graph big enough that every CTA wraps its 4-stage ring
+    many times (LMD16, 48 sequences: ~25k nodes, ~85k edges -> ~18 stages per CTA), structured layout with node_order
+    and padding rows: gx bit-identical to the legacy two-kernel path, table gradient equal to fp32 accumulation
+    order, bit-reproducible."""
+    import polyphemus_b200 as pb
+    ffi = _ffi()
+    s_np = go.synthetic_structure(48, 16, 0.25, seed=9)
+    g = pb.graphs_from_tensor(torch.from_numpy(s_np).to(cuda))
+    stp = g.structured
+    plan, n, k, e = stp.plan, stp.n_padded, 4 * d, g.num_edges
+    gen = torch.Generator().manual_seed(d)
+    valid = torch.zeros(n, dtype=torch.bool)
+    valid[stp.pos.cpu()] = True
+    x = (torch.randn(n, d, generator=gen) * valid.unsqueeze(1)).to(cuda).to(torch.bfloat16)
+    gy = (torch.randn(n, d, generator=gen) * valid.unsqueeze(1)).to(cuda).to(torch.bfloat16)
+    d_a = (torch.randn(n, k, generator=gen) * valid.unsqueeze(1)).to(cuda).to(torch.bfloat16)
+    table = (torch.randn(32, d, generator=gen) * 0.5).to(cuda)
+    p_drop, seed = 0.1, 77
+    bits = keep_bits(e, d, p_drop, seed, cuda)
+    lib = ffi.lib()
+    # legacy
+    gx0 = torch.empty(n, d, dtype=torch.bfloat16, device=cuda)
+    q_buf = torch.empty(e, d, dtype=torch.bfloat16, device=cuda)
+    parts0 = torch.empty(plan.n_dist_items, d, device=cuda)
+    ffi.check(lib.pb_agg_bwd(plan.ref(), ptr(x), d, ptr(table), ptr(d_a), k, ffi.PB_BF16, ptr(gy), ptr(gx0), ptr(q_buf), ptr(parts0),
+                             ptr(bits), p_drop, ffi.PB_BF16, st()), "agg_bwd")
+    gw0, gb0 = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+    ffi.check(lib.pb_edge_table_bwd(ptr(parts0), ptr(plan.dist_item_ptr), d, ptr(gw0), ptr(gb0), st()), "table_bwd")
+    # tensor-core path
+    n_part = lib.pb_agg_bwd_num_partials(n, d, ffi.PB_BF16)
+    outs = []
+    for _ in range(2):
+        gx1 = torch.full((n, d), float("nan"), dtype=torch.bfloat16, device=cuda)
+        parts1 = torch.full((n_part, 32, d), float("nan"), device=cuda)
+        ffi.check(lib.pb_agg_bwd_fused(plan.ref(), ptr(x), d, ptr(table), ptr(d_a), k, ffi.PB_BF16, ptr(gy), ptr(gx1), ptr(parts1),
+                                       ptr(bits), p_drop, ffi.PB_BF16, st()), "agg_bwd_fused")
+        gw1, gb1 = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+        ffi.check(lib.pb_edge_table_bwd_fused(ptr(parts1), n_part, d, ptr(gw1), ptr(gb1), st()), "table_bwd_fused")
+        outs.append((gx1, parts1, gw1, gb1))
+    (gx1, parts1, gw1, gb1), (gx2, parts2, gw2, gb2) = outs
+    assert torch.equal(gx1, gx0)
+    assert torch.equal(gx1, gx2) and torch.equal(parts1, parts2) and torch.equal(gw1, gw2)
+    # both paths sum the same bf16-rounded rows in fp32, in different orders
+    scale = float(gw0.abs().max())
+    torch.testing.assert_close(gw1, gw0, rtol=1e-4, atol=2e-5 * scale)
+    torch.testing.assert_close(gb1, gb0, rtol=1e-4, atol=2e-4 * scale)
+    # and against the exact sum of the rows the legacy path left in q_buf
+    ref = torch.zeros(32, d, dtype=torch.float64, device=cuda)
+    dist_of_pos = ((plan.out_rec[:e, 1] >> 8) & 31).long()
+    ref.index_add_(0, dist_of_pos, q_buf.double())
+    torch.testing.assert_close(gw1.double().t(), ref, rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_agg_bwd_fused_foreign_graph_high_degree(cuda):
+    """Arbitrary edge list (out-degree far above the 8 pipelined slots, self-loops, isolated nodes): the unpipelined
+    tail of the fused backward and the generic 6-relation plan against autograd in fp64."""
+    from types import SimpleNamespace
+    from polyphemus_b200.graph import CsrPlan
+
+    ffi = _ffi()
+    n, e, d = 150, 4000, 128
+    gen = torch.Generator().manual_seed(5)
+    ei = torch.randint(0, n - 10, (2, e), generator=gen)            # the last 10 nodes are isolated
+    ei[:, :50] = 3                                                  # 50 parallel self-loops on node 3
+    et = torch.randint(0, 6, (e,), generator=gen, dtype=torch.uint8)
+    ed = torch.randint(0, 32, (e,), generator=gen, dtype=torch.uint8)
+    arrays = SimpleNamespace(edge_index=ei.numpy(), edge_type=et.long().numpy(), edge_dist=ed.long().numpy())
+    plan = CsrPlan(ei.to(cuda), et.to(cuda), ed.to(cuda), n)
+    k = 7 * d
+    x = torch.randn(n, d, generator=gen, dtype=torch.float64).float().double().requires_grad_(True)
+    table = (torch.randn(32, d, generator=gen, dtype=torch.float64) * 0.5).float().double().requires_grad_(True)
+    d_a = torch.randn(n, k, generator=gen, dtype=torch.float64).float().double()
+    gy = torch.randn(n, d, generator=gen, dtype=torch.float64).float().double()
+    a_ref = torch.cat((_oracle_h(x, arrays, table), x), 1)
+    (a_ref * d_a).sum().backward()
+    x_dev, t_dev, gy_dev, da_dev = (v.detach().float().to(cuda) for v in (x, table, gy, d_a))
+    n_part = ffi.lib().pb_agg_bwd_num_partials(n, d, ffi.PB_F32)
+    parts = torch.empty((n_part, 32, d), device=cuda)
+    gx = torch.empty(n, d, device=cuda)
+    ffi.check(ffi.lib().pb_agg_bwd_fused(plan.ref(), ptr(x_dev), d, ptr(t_dev), ptr(da_dev), k, ffi.PB_F32, ptr(gy_dev), ptr(gx),
+                                         ptr(parts), None, 0.0, ffi.PB_F32, st()), "agg_bwd_fused")
+    torch.testing.assert_close(gx.double().cpu(), x.grad + gy, rtol=1e-5, atol=1e-5)
+    g_w, g_b = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+    ffi.check(ffi.lib().pb_edge_table_bwd_fused(ptr(parts), n_part, d, ptr(g_w), ptr(g_b), st()), "table_bwd_fused")
+    scale = max(1.0, float(table.grad.abs().max()))
+    torch.testing.assert_close(g_w.double().cpu(), table.grad.t(), rtol=1e-5, atol=1e-5 * scale)
 
 
 # ------------------------------------------------------------------------------------------------- BatchNorm
