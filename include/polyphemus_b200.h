@@ -345,6 +345,26 @@ int pb_bar_expand_fwd(const float* z, const int32_t* bar_ptr, int64_t n_bars, in
 int pb_bar_expand_bwd(const float* g_x, int64_t ldg, const int32_t* bar_ptr, int64_t n_bars, int32_t d, float* g_z,
                       pb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Data formats either side of the path.
+ *   pb_dataset_structure / pb_dataset_tokens — replace PolyphemusDataset.__getitem__ (data.py:218-271) for a batch of
+ *     samples in the on-disk layout of preprocess.py:210: s_disk u8/bool [B, 4, T], c_disk int16 [B, 4, T, 16, 2],
+ *     T = n_bars * 32. Step 1 reorders the structure to [B, n_bars, 4, 32] (data.py:230-231); pb_graph_count then
+ *     applies the fake activation of empty bars and yields bar_bits / node_ptr; step 2 copies the 16 (pitch, duration)
+ *     pairs of every active cell into tokens int16 [N, 16, 2] in node order — the silence filter of data.py:264-266.
+ *     The one-hot expansion (data.py:233-259) is not materialised: token ids feed pb_chord_embed_fwd directly.
+ *   pb_mtp_from_logits — replaces utils.mtp_from_logits (utils.py:59-79): mtp [n_cells, n_tok, d_tok] (f32 or bf16,
+ *     cells = flattened [B, n_bars, 4, 32]); an active cell (s_tensor != 0) takes the logits of node node_of_cell[cell]
+ *     (= number of active cells before it), a silent one the silence pattern (token 0: pitch_eos, others: pitch_pad).
+ * ---------------------------------------------------------------------------------------------- */
+int pb_dataset_structure(const uint8_t* s_disk, int64_t n_samples, int32_t n_bars, uint8_t* s_tensor,
+                         pb_stream_t stream);
+int pb_dataset_tokens(const int16_t* c_disk, const uint32_t* bar_bits, const int32_t* node_ptr, int64_t n_samples,
+                      int32_t n_bars, int16_t* tokens, pb_stream_t stream);
+int pb_mtp_from_logits(const void* c_logits, int64_t ld_node, int32_t dtype, const uint8_t* s_tensor,
+                       const int32_t* node_of_cell, int64_t n_cells, int32_t n_tok, int32_t d_tok, int32_t pitch_eos,
+                       int32_t pitch_pad, void* mtp, pb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

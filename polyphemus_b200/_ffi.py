@@ -96,6 +96,9 @@ SIGNATURES = {
     "pb_ce_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
     "pb_ce_rows_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "pb_ce_rows_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "pb_dataset_structure": (c_int, [_P, c_int64, c_int32, _P, _P]),
+    "pb_dataset_tokens": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P]),
+    "pb_mtp_from_logits": (c_int, [_P, c_int64, c_int32, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),
 }
 
 _lib = None

@@ -255,7 +255,7 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
     g = Graph(edge_index=edge_index, edge_type=edge_type, edge_dist=edge_dist, node_features=node_features,
               is_drum=is_drum, bars=bars, batch=batch, num_nodes=n, num_edges=e, num_graphs=bsz, n_bars=n_bars,
               n_drum=n_drum, node_track=node_track, node_group=node_group, group_counts=group_counts,
-              bar_ptr=node_ptr)
+              bar_ptr=node_ptr, bar_bits=bar_bits)
     if edge_attrs is not None:
         g._edge_attrs = edge_attrs
     return g

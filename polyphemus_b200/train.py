@@ -89,13 +89,33 @@ def _masked_ce(logits, target: torch.Tensor, ignore_index: int) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------ synthetic data
 @dataclass
 class HostBatch:
-    """What a data loader would hand over: pinned host memory in the dataset's compact layout."""
+    """What a data loader would hand over: pinned host memory, either compacted (structure + the active cells'
+    tokens) or — ``c_disk`` / ``s_disk`` — the samples exactly as preprocess.py:210 stores them on disk."""
     s_tensor: torch.Tensor      # bool  [B, n_bars, 4, 32]
     tokens: torch.Tensor        # int16 [N, 16, 2]  (pitch id, duration id) for every active (bar, track, t)
+    c_disk: Optional[torch.Tensor] = None    # int16 [B, 4, T, 16, 2]   on-disk c_tensor of every sample
+    s_disk: Optional[torch.Tensor] = None    # bool  [B, 4, T]          on-disk s_tensor of every sample
 
     @property
     def nbytes(self) -> int:
+        if self.c_disk is not None:
+            return self.c_disk.numel() * self.c_disk.element_size() + self.s_disk.numel() * self.s_disk.element_size()
         return self.s_tensor.numel() * self.s_tensor.element_size() + self.tokens.numel() * self.tokens.element_size()
+
+
+def disk_layout(s_tensor: torch.Tensor, tokens: torch.Tensor):
+    """(c_disk int16 [B, 4, T, 16, 2], s_disk bool [B, 4, T]) holding the given batch the way preprocess.py writes
+    samples: silent cells carry [SOS, EOS, PAD, ...] (preprocess.py:120-147), active cells their tokens."""
+    bsz, n_bars = s_tensor.shape[:2]
+    s = s_tensor.bool()
+    cells = torch.empty((bsz, n_bars, 4, 32, MAX_SIMU_TOKENS, 2), dtype=torch.int16)
+    cells[..., 0], cells[..., 1] = PITCH_PAD, DUR_PAD
+    cells[..., 0, 0], cells[..., 0, 1] = PITCH_SOS, DUR_SOS
+    cells[..., 1, 0], cells[..., 1, 1] = PITCH_EOS, DUR_EOS
+    cells[s] = tokens.to(torch.int16)
+    c_disk = cells.permute(0, 2, 1, 3, 4, 5).reshape(bsz, 4, n_bars * 32, MAX_SIMU_TOKENS, 2).contiguous()
+    s_disk = s.permute(0, 2, 1, 3).reshape(bsz, 4, n_bars * 32).contiguous()
+    return c_disk, s_disk
 
 
 def synthetic_tokens(num_nodes: int, generator: torch.Generator) -> torch.Tensor:
@@ -113,17 +133,27 @@ def synthetic_tokens(num_nodes: int, generator: torch.Generator) -> torch.Tensor
     return torch.stack((pitch, dur), dim=-1).to(torch.int16)
 
 
-def synthetic_host_batch(batch: int, n_bars: int, p: float = 0.25, seed: int = 0, pin: bool = True) -> HostBatch:
+def synthetic_host_batch(batch: int, n_bars: int, p: float = 0.25, seed: int = 0, pin: bool = True,
+                         disk: bool = False) -> HostBatch:
+    """``disk=True`` also lays the batch out as on-disk samples (the empty bars are then left empty in ``s_disk``: the
+    fake activation is the decoder's job, data.py:152-153)."""
     rng = np.random.default_rng(seed)
     s = rng.random((batch, n_bars, 4, 32)) < p
+    s_raw = s.copy()
     empty = ~s.reshape(batch, n_bars, -1).any(axis=-1)
     s[empty, 0, 0] = True                       # the dataset applies data.py:152-153 before filtering c_tensor
     n = int(s.sum())
     tokens = synthetic_tokens(n, torch.Generator().manual_seed(seed))
     s_t = torch.from_numpy(s)
+    c_disk = s_disk = None
+    if disk:
+        c_disk, _ = disk_layout(s_t, tokens)
+        s_disk = torch.from_numpy(s_raw).permute(0, 2, 1, 3).reshape(batch, 4, n_bars * 32).contiguous()
     if pin and torch.cuda.is_available():
         s_t, tokens = s_t.pin_memory(), tokens.pin_memory()
-    return HostBatch(s_t, tokens)
+        if disk:
+            c_disk, s_disk = c_disk.pin_memory(), s_disk.pin_memory()
+    return HostBatch(s_t, tokens, c_disk, s_disk)
 
 
 def onehot_content(tokens: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
@@ -139,6 +169,9 @@ def onehot_content(tokens: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
 def device_batch(host: HostBatch, device, onehot: bool = False, onehot_dtype=torch.float32) -> Graph:
     """Host batch -> device graph with ``s_tensor`` and ``c_tokens`` attached (H2D copies + device graph
     build). ``onehot=True`` also expands the reference's ``c_tensor`` one-hot layout on the device."""
+    if host.c_disk is not None:          # samples as stored on disk: bars reshape, silence filter etc. on the device
+        from .data import decode_samples
+        return decode_samples(host.c_disk, host.s_disk, int(host.s_tensor.size(1)), device=device, onehot=onehot)
     s_dev = host.s_tensor.to(device, non_blocking=True)
     tok_dev = host.tokens.to(device, non_blocking=True)
     graph = graphs_from_tensor(s_dev)

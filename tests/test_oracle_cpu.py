@@ -131,3 +131,70 @@ def test_oracle_against_live_reference():
     ei = torch.tensor([[0, 1, 2, 2, 4], [1, 1, 1, 3, 3]])
     out = conv.propagate(ei, x=x, size=(5, 5))
     assert torch.allclose(out[1], x[[0, 1, 2]].mean(0)) and torch.allclose(out[3], x[[2, 4]].mean(0)) and out[0].abs().sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ data formats
+def _dataset_cases():
+    ref = golden("dataset_items.npz")
+    keys = sorted({k.rsplit(".", 1)[0] for k in ref.files})
+    return ref, keys
+
+
+def test_dataset_item_oracle_matches_reference_golden():
+    """oracle.data_oracle.dataset_item == PolyphemusDataset.__getitem__ (data.py:218-271) on on-disk-layout samples
+    (empty bar, full bar, single-node bar; LMD2 and LMD16 shapes)."""
+    from oracle import data_oracle as do
+
+    ref, keys = _dataset_cases()
+    assert len(keys) == 8
+    for key in keys:
+        n_bars = int(key.split(".")[0][1:])
+        s, tokens, arrays = do.dataset_item(ref[key + ".c_disk"], ref[key + ".s_disk"], n_bars)
+        np.testing.assert_array_equal(s, ref[key + ".s_tensor"])
+        np.testing.assert_array_equal(tokens, ref[key + ".tokens"].astype(np.int64))
+        np.testing.assert_array_equal(arrays.edge_index, ref[key + ".edge_index"])
+        assert arrays.num_nodes == int(ref[key + ".num_nodes"]) == tokens.shape[0]
+
+
+def test_mtp_from_logits_oracle_matches_reference_golden():
+    from oracle import data_oracle as do
+
+    ref = golden("mtp_from_logits.npz")
+    mtp = do.mtp_from_logits(ref["c_logits"], ref["s_tensor"])
+    assert mtp.shape == ref["s_tensor"].shape + (15, 230)
+    np.testing.assert_array_equal(mtp[ref["s_tensor"]], ref["c_logits"])
+    np.testing.assert_allclose(mtp.sum(-1), ref["mtp_sum"], rtol=0, atol=1e-5)
+    silent = ~ref["s_tensor"]
+    np.testing.assert_array_equal(mtp.argmax(-1)[silent], ref["mtp_argmax"][silent])
+    assert (mtp[silent][:, 0].argmax(-1) == 129).all() and (mtp[silent][:, 1:].argmax(-1) == 130).all()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present (GPU box)")
+def test_data_oracle_against_live_reference(tmp_path):
+    """Container only: the same two restatements against the reference's own code on fresh random samples."""
+    import importlib
+    import os
+
+    from oracle import data_oracle as do
+
+    ref = ref_loader.load()
+    rng = np.random.default_rng(123)
+    n_bars, t_len = 4, 128
+    s = rng.random((4, t_len)) < 0.2
+    s[:, 32:64] = False
+    c = rng.integers(0, 96, (4, t_len, 16, 2)).astype(np.int16)
+    np.savez(tmp_path / "x0", c_tensor=c, s_tensor=s)
+    g = ref.data.PolyphemusDataset(str(tmp_path), n_bars=n_bars)[0]
+    s_o, tok_o, arrays = do.dataset_item(c, s, n_bars)
+    np.testing.assert_array_equal(s_o, g.s_tensor.numpy().astype(bool))
+    np.testing.assert_array_equal(do.onehot(tok_o), g.c_tensor.numpy())
+    np.testing.assert_array_equal(arrays.edge_index, g.edge_index.numpy())
+    cwd = os.getcwd()
+    os.chdir(ref_loader.REFERENCE_DIR)
+    try:
+        utils = importlib.import_module("utils")
+    finally:
+        os.chdir(cwd)
+    st = torch.from_numpy(s_o[None])
+    logits = torch.randn(int(st.sum()), 15, 230, generator=torch.Generator().manual_seed(1))
+    np.testing.assert_array_equal(do.mtp_from_logits(logits.numpy(), st.numpy()), utils.mtp_from_logits(logits, st).numpy())
