@@ -76,8 +76,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_oracle_step_factory(batch: int, n_bars: int, seed: int = 0):
-    """One fwd + loss + bwd of the oracle port (reference algorithm, plain PyTorch CPU) on a bounded sample."""
+def cpu_oracle_step_factory(batch: int, n_bars: int, gcl_dropout: float, seed: int = 0):
+    """One graph build + fwd + loss + bwd of the oracle port (the reference's algorithm in plain PyTorch on the CPU:
+    per-relation boolean compaction, Linear on one-hot distances, index_add scatter-mean, seven matmuls per layer,
+    model.py:103-135) on a bounded sample. The GCL message dropout is drawn exactly as the reference draws it
+    (F.dropout on every relation's E_r x d message tensor, model.py:133) — the same workload as the GPU arm."""
     from oracle import graph_oracle as go
     from oracle import model_oracle as mo
     import polyphemus_b200 as pb
@@ -92,21 +95,21 @@ def cpu_oracle_step_factory(batch: int, n_bars: int, seed: int = 0):
         arrays = go.batch_graph(s_np)                               # graph construction is part of the step
         tokens = mo.synthetic_tokens(arrays.num_nodes, seed)
         gb = mo.make_batch(arrays, tokens)
-        ctx = mo.Ctx(training=True)
+        ctx = mo.Ctx(training=True, gcl_dropout=gcl_dropout, gcl_random_dropout=gcl_dropout > 0)
         (s_logits, c_logits), mu, log_var = mo.vae(sd, gb, n_bars, cfg["d"], ctx)
         loss, _ = mo.losses(gb.s_tensor, s_logits, gb.c_tensor, c_logits, mu, log_var)
         for v in sd.values():
             if v.grad is not None:
                 v.grad = None
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     return step
 
 
-def time_cpu_baseline(batch: int, n_bars: int, steps: int, warmup: int):
+def time_cpu_baseline(batch: int, n_bars: int, steps: int, warmup: int, gcl_dropout: float):
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_oracle_step_factory(batch, n_bars)
+    step = cpu_oracle_step_factory(batch, n_bars, gcl_dropout)
     for _ in range(warmup):
         step()
     times = []
@@ -117,21 +120,54 @@ def time_cpu_baseline(batch: int, n_bars: int, steps: int, warmup: int):
     return batch / min(times), times
 
 
+def cpu_graph_build_ms_per_bar(n_bars: int = 16, seqs: int = 4) -> float:
+    """data.graph_from_tensor's algorithm (oracle.graph_oracle, numpy) on one core: ms per bar."""
+    from oracle import graph_oracle as go
+
+    torch.set_num_threads(1)
+    s_np = go.synthetic_structure(seqs, n_bars, DENSITY, 0)
+    go.batch_graph(s_np[:1])
+    t0 = time.perf_counter()
+    go.batch_graph(s_np)
+    dt = time.perf_counter() - t0
+    torch.set_num_threads(os.cpu_count() or 1)
+    return 1e3 * dt / (seqs * n_bars)
+
+
+def cpu_baseline_block(args) -> dict:
+    """LMD16 batch 8 (the metric's sequence shape), config 1 exactly (LMD2, batch 64), graph
+    construction ms/bar — all on this box's host cores, GCL dropout as in the GPU arm."""
+    v16, t16 = time_cpu_baseline(args.cpu_batch, MODEL_CFG["n_bars"], 2, 1, args.gcl_dropout)
+    v2, t2 = time_cpu_baseline(64, 2, 2, 1, args.gcl_dropout)
+    return {"value": v16, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle port (reference algorithm, PyTorch CPU fp32, GCL dropout {args.gcl_dropout} drawn as "
+                      f"model.py:133), LMD16 batch {args.cpu_batch}: graph build + fwd + loss + bwd, best of {len(t16)} "
+                      f"after 1 warm-up ({min(t16):.2f} s/step)",
+            "config1_lmd2_batch64": {"value": v2, "unit": "seq/s", "s_per_step": min(t2),
+                                     "sample": "BASELINE.json configs[0]: LMD2, batch 64, fwd + loss + bwd, best of 2 after 1 warm-up"},
+            "graph_build_ms_per_bar": cpu_graph_build_ms_per_bar(),
+            "same_config_as_gpu_arm": {"model": True, "gcl_dropout": True, "batch": False},
+            "note": "the port is ~7x faster than the reference's own files measured at survey time (BASELINE.md §2: "
+                    "1.4 seq/s LMD16 batch 8, 12.9 seq/s LMD2 batch 64, 3.3-4.1 ms/bar on 8 vCPU)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     batch = args.cpu_batch
     t_all = time.perf_counter()
-    value, times = time_cpu_baseline(batch, MODEL_CFG["n_bars"], max(1, args.steps), max(0, min(args.warmup, 1)))
+    value, times = time_cpu_baseline(batch, MODEL_CFG["n_bars"], max(1, args.steps), max(0, min(args.warmup, 1)),
+                                     args.gcl_dropout)
     ms = 1e3 * statistics.mean(times)
-    sample = (f"oracle port (reference algorithm, PyTorch CPU fp32) of the LMD16 step on batch {batch} "
-              f"(graph build + fwd + loss + bwd), best of {len(times)}")
+    sample = (f"oracle port (reference algorithm, PyTorch CPU fp32, GCL dropout {args.gcl_dropout}) of the LMD16 step on "
+              f"batch {batch} (graph build + fwd + loss + bwd), best of {len(times)}")
     line = {
         "impl": "reference", "metric": "LMD16 train seqs/s", "value": value, "unit": "seq/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": batch, "n_bars": 16, "d": 512, "gnn_n_layers": 8},
+        "config": {"workload": WORKLOAD, "batch": batch, "n_bars": 16, "d": 512, "gnn_n_layers": 8,
+                   "gcl_dropout": args.gcl_dropout},
         "cpu_baseline": {"value": value, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": time.perf_counter() - t_all,
@@ -203,6 +239,179 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
     return rows
 
 
+# ------------------------------------------------------------------------------------------------ secondary configs
+def _timed_ms(fn, iters, world=1):
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms)
+
+
+def _train_ms(batch, precision, dev, world, rank, args, warm=3, iters=4):
+    """ms/step of the LMD16 training step at `batch` sequences per GPU (device graph build included, no prefetch)."""
+    import polyphemus_b200 as pb
+    from polyphemus_b200.train import TrainStep, device_batch, synthetic_host_batch
+
+    pb.set_precision(precision)
+    torch.manual_seed(0)
+    model = pb.VAE(**MODEL_CFG, device=dev).to(dev).train()
+    for m in model.modules():
+        if isinstance(m, pb.GCL):
+            m.dropout = args.gcl_dropout
+    step = TrainStep(model, autocast_bf16=precision == "bf16", **ADAM)
+    host = synthetic_host_batch(batch, MODEL_CFG["n_bars"], DENSITY, seed=7 + rank)
+    try:
+        fn = lambda: step(device_batch(host, dev))
+        for _ in range(warm):
+            fn()
+        ms = _timed_ms(fn, iters, world)
+        return {"per_gpu_batch": batch, "global_batch": batch * world, "ms_per_step": ms, "seq_per_s": batch * world / ms * 1e3,
+                "nodes_per_gpu": int(host.tokens.size(0)), "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2**30}
+    finally:
+        step.close()
+        pb.set_precision(args.precision)
+
+
+def _layer_point(target_e, d, precision, dev, pk, p_drop=0.1):
+    """One GCN layer (GCL + BatchNorm + ReLU + residual, model.py:198-206) fwd + bwd in isolation on an LMD-shaped
+    graph with ~target_e edges, called on the stack's own (structured, padded) layout so that only the layer's
+    kernels run."""
+    import polyphemus_b200 as pb
+    from polyphemus_b200 import _ffi
+
+    n_bars = max(16, int(target_e / 112) // 16 * 16)              # ~112 edges per bar at p = 0.25
+    gen = torch.Generator(device=dev).manual_seed(0)
+    s = torch.rand((n_bars // 16, 16, 4, 32), device=dev, generator=gen) < DENSITY
+    graph = pb.graphs_from_tensor(s)
+    del s
+    n, e = graph.num_nodes, graph.num_edges
+    st = graph.structured
+    bf16 = precision == "bf16"
+    gcn = pb.GCN(input_dim=d, hidden_dim=d, n_layers=1, num_relations=6, batch_norm=True, dropout=0, precision=precision).to(dev).train()
+    layer, bn = gcn.layers[0], gcn.norm_layers[0].module
+    layer.dropout = p_drop
+    adt = torch.bfloat16 if bf16 else torch.float32
+    x = torch.randn(st.n_padded, d, device=dev, dtype=adt).requires_grad_(True)
+    gy = torch.randn(st.n_padded, d, device=dev, dtype=adt)
+
+    def step():
+        layer(x, plan=st.plan, bn=bn, struct=st).backward(gy)
+        x.grad = None
+
+    for _ in range(2):
+        step()
+    _ffi.profiler.reset()
+    _ffi.profiler.enabled = True
+    iters = 3
+    ms = _timed_ms(step, iters)
+    _ffi.profiler.enabled = False
+    summ = _ffi.profiler.summary()
+    rows = kernel_table(summ, n, e, d, iters, precision, pk, p_drop, slots=3, n_rows=st.n_padded, act_bytes=2 if bf16 else 4)
+    hb = [r for r in rows if r["bound"] == "hbm"]
+    hbm_ms = sum(r["ms_per_step"] for r in hb)
+    hbm_bytes = sum(r["algorithmic_per_launch"] * r["launches_per_step"] for r in hb)
+    return {"edges": e, "nodes": n, "d": d, "precision": precision, "gcl_dropout": p_drop, "ms_fwd_bwd": ms,
+            "hbm_kernels_frac": hbm_bytes / (hbm_ms * 1e-3) / 1e9 / pk["hbm"] if hbm_ms else None,
+            "kernels": {r["kernel"]: round(r["frac"], 3) for r in rows if r["frac"] is not None},
+            "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2**30}
+
+
+def secondary_measurements(args, dev, world, rank, pk):
+    """The other BASELINE.json configurations, short runs (a few steps each) after the headline measurement:
+    configs[1] fp32 arm, configs[2] LMD2 generation of 4096 sequences to the pianoroll tensor, configs[3] isolated
+    layer sweep up to 1e8 edges (N = 1 only), configs[4] per-GPU batch 512 .. 2048 at this N. Failures (e.g. out of
+    memory at the largest points) are recorded, never fatal."""
+    import gc
+    import numpy as np
+    import torch.distributed as dist
+    import polyphemus_b200 as pb
+
+    out = {}
+
+    def guarded(name, fn):
+        gc.collect()
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        ok = 1
+        try:
+            res = fn()
+        except Exception as exc:   # noqa: BLE001 - recorded in the JSON line
+            res, ok = {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}, 0
+        if world > 1:              # every rank must agree before the next collective-bearing measurement
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag) == 0 and ok:
+                res = {"error": "another rank failed"}
+        out[name] = res
+        return ok
+
+    # configs[4]: large per-GPU batches at this N (weak scaling, NCCL all-reduce inside the step)
+    for b in (512, 1024, 2048):
+        gc.collect()
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0] / 2**30
+        need = {512: 50, 1024: 85, 2048: 150}[b]
+        enough = torch.tensor([1 if free > need else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(enough, op=dist.ReduceOp.MIN)
+        if int(enough) == 0:
+            out[f"large_batch_{b}"] = {"skipped": f"{free:.0f} GiB free < {need} GiB needed"}
+            continue
+        if not guarded(f"large_batch_{b}", lambda: _train_ms(b, "bf16", dev, world, rank, args, warm=2, iters=3)):
+            break
+    if world == 1:
+        # configs[1], fp32 arm: the parity mode (TF32x3 on the tensor cores) on the headline workload
+        guarded("fp32_mode_batch256", lambda: _train_ms(args.batch, "fp32", dev, 1, rank, args, warm=2, iters=3))
+
+        # configs[2]: LMD2 decoder-only generation of 4096 sequences with structure conditioning, down to the
+        # [4096, 2, 4, 32, 15, 230] pianoroll tensor (generate.py:24-35, 226-237, utils.py:59-79)
+        def gen():
+            cfg = dict(MODEL_CFG, n_bars=2)
+            pb.set_precision("bf16")
+            torch.manual_seed(0)
+            vae = pb.VAE(**cfg, device=dev).to(dev).eval()
+            s_json = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden", "graph_structure_json.npz"))["s_in"][0]).bool()
+            n = 4096
+            s_cond = s_json.unsqueeze(0).repeat(n, 1, 1, 1).to(dev)
+
+            def run():
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    z = torch.randn(n, cfg["d"], device=dev)
+                    graph = vae.decoder._structure_from_binary(s_cond.clone())
+                    _, c_logits = vae.decoder(z, graph)
+                    return pb.mtp_from_logits(c_logits.to(torch.bfloat16), s_cond)
+
+            for _ in range(2):
+                mtp = run()
+            ms = _timed_ms(run, 3)
+            res = {"sequences": n, "ms": ms, "seq_per_s": n / ms * 1e3, "nodes": int(s_cond.sum()),
+                   "mtp_shape": list(mtp.shape), "mtp_dtype": "bf16", "peak_mem_gib": torch.cuda.max_memory_allocated(dev) / 2**30}
+            pb.set_precision(args.precision)
+            return res
+        guarded("generation_lmd2_4096", gen)
+
+        # configs[3]: isolated layer sweep
+        for target_e, d, precision, p_drop in ((1e5, 512, "bf16", 0.1), (1e6, 256, "bf16", 0.1), (1e6, 512, "bf16", 0.1),
+                                               (1e6, 1024, "bf16", 0.1), (1e6, 512, "fp32", 0.1), (1e7, 512, "bf16", 0.1),
+                                               (1e7, 1024, "bf16", 0.1), (3e7, 256, "bf16", 0.1), (1e8, 256, "bf16", 0.0)):
+            guarded(f"layer_E{target_e:.0e}_d{d}_{precision}".replace("+0", ""),
+                    lambda: _layer_point(target_e, d, precision, dev, pk, p_drop))
+    pb.set_precision(args.precision)
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -214,6 +423,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-batch", type=int, default=8, help="bounded CPU sample (sequences)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary BASELINE.json configurations")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs: skip the second (host-fed) timed region")
     ap.add_argument("--profiler-range", action="store_true",
                     help="bracket the first timed region with cudaProfilerStart/Stop (ncu --profile-from-start off)")
@@ -251,7 +461,10 @@ def main():
 
     # a few distinct batches so the step cannot specialise on one graph; each rank gets its own shard
     n_variants = 2
-    hosts = [synthetic_host_batch(args.batch, MODEL_CFG["n_bars"], DENSITY, seed=1000 * rank + i) for i in range(n_variants)]
+    # e2e input = the samples exactly as they lie on disk (preprocess.py:210: int16 c_tensor [4, T, 16, 2] + bool s_tensor
+    # [4, T] per sample), pinned; bars reshape / fake activations / silence filter / graph build happen on the device
+    hosts = [synthetic_host_batch(args.batch, MODEL_CFG["n_bars"], DENSITY, seed=1000 * rank + i, disk=True)
+             for i in range(n_variants)]
     resident = [(h.s_tensor.to(dev), h.tokens.to(dev)) for h in hosts]
 
     # Every step builds its graph on the device; the build of step i+1 is issued on a side stream before step i is
@@ -310,7 +523,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     _ffi.profiler.reset()
     _ffi.profiler.reserve(500 * args.steps)          # ~375 library calls per step: no event creation in the timed region
-    _ffi.profiler.enabled = True
+    _ffi.profiler.enabled = os.environ.get("PB200_NO_EVENTS") != "1"
     launches0 = _ffi.launch_counter["n"]
     if args.profiler_range:
         torch.cuda.profiler.start()
@@ -323,6 +536,12 @@ def main():
     # ---- timed region 2: end to end from pinned host memory
     e2e_ms = total_ms if args.skip_e2e else timed(step_e2e, args.steps)
     clocks = sampler.stop() if sampler else None
+
+    step_fn.close()
+    secondary = None
+    if not args.no_secondary:
+        del step_fn, model, resident, pending
+        secondary = secondary_measurements(args, dev, world, rank, pk)
 
     n_nodes = sum(h.tokens.size(0) for h in hosts) / n_variants
     graph0 = device_batch(hosts[0], dev)
@@ -381,10 +600,7 @@ def main():
                     "share_of_step": hb["ms_per_step"] / (total_ms / args.steps)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:      # reported on rank 0 at N=1 only (the other ranks would wait)
-            v, times = time_cpu_baseline(args.cpu_batch, MODEL_CFG["n_bars"], 2, 1)
-            cpu = {"value": v, "unit": "seq/s", "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"oracle port (reference algorithm, PyTorch CPU fp32), LMD16 batch {args.cpu_batch}: graph build + "
-                             f"fwd + loss + bwd, best of {len(times)} after 1 warm-up ({min(times):.2f} s/step)"}
+            cpu = cpu_baseline_block(args)
         line = {
             "metric": "LMD16 train seqs/s", "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -399,12 +615,15 @@ def main():
                        "l2": "per-step working set (several GB of activations) exceeds the 126 MB L2; no explicit flush",
                        "step": "device graph build + fwd + loss + bwd + NCCL grad all-reduce + Adam"},
             "e2e": {"value": e2e_value, "unit": "seq/s", "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": hosts[0].nbytes, "d2h_bytes_per_step": 4 + 32},
+                    "h2d_bytes_per_step": hosts[0].nbytes, "d2h_bytes_per_step": 4 + 64,
+                    "input": "pinned host buffers in the dataset's on-disk sample layout (int16 c_tensor [B,4,T,16,2], bool "
+                             "s_tensor [B,4,T]); decode + graph build on the device (pb.decode_samples)"},
             "gpu_launches": launches, "roofline": roofline,
             "mp_layer_hbm": {"achieved": hbm_bytes / (hbm_ms * 1e-3) / 1e9 if hbm_ms else None, "peak": pk["hbm"],
                              "unit": "GB/s", "frac": hbm_bytes / (hbm_ms * 1e-3) / 1e9 / pk["hbm"] if hbm_ms else None,
                              "note": "all HBM-bound message-passing kernels (aggregate fwd/bwd, BN/ReLU/residual fwd/bwd)"},
             "kernels": rows, "our_kernels_ms_per_step": ours_ms, "cpu_baseline": cpu, "clocks": clocks,
+            "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

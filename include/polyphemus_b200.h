@@ -237,7 +237,8 @@ int pb_gemm_nt(const void* a_hi, const void* a_lo, int64_t lda, const void* b_hi
                const float* bias, void* out, int64_t ldo, int64_t m, int32_t n, int32_t k, int32_t dtype,
                int32_t out_bf16, pb_stream_t stream);
 /* dWcat f32 [K,d] = A^T @ g (fixed-order split-K over the node dimension, deterministic). */
-size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k);
+size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k);            /* any dtype */
+size_t pb_rgcn_gemm_bwd_weight_workspace_bytes_for(int64_t m, int32_t d, int32_t k, int32_t dtype);   /* PB_BF16 needs no transposed copies */
 /* Structured form (groups != NULL, k == 4d): d_wcat is the full [(R+1)d, d]; the split boundaries follow the row
  * groups, the track block of the partials is reduced per group into weight[g], the other blocks over all rows. */
 int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
@@ -324,6 +325,11 @@ int pb_ce_rows_bwd(const void* logits, int64_t ld, int32_t dtype, int64_t rows, 
 int pb_chord_embed_fwd(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots,
                        const uint8_t* set_id, const void* tables, int32_t dtype, int32_t vocab, int32_t dur_off,
                        int32_t d, const float* bias, float* chord, int64_t ldc, int64_t n_nodes, pb_stream_t stream);
+/* Token histograms per table set (0 = non-drum, 1 = drum nodes) over the n_slots (pitch, duration) pairs from tok_offset:
+ * counts i64 [2, n_pitch + n_dur] (pitch bins first). They weight the BatchNorm statistics of the folded embedding
+ * tables (BatchNorm over Linear(one_hot) rows, model.py:355-376). Exact integer counts, no host read-back. */
+int pb_token_hist(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots, const uint8_t* set_id,
+                  int64_t n_nodes, int32_t n_pitch, int32_t n_dur, int64_t* counts, pb_stream_t stream);
 int pb_chord_embed_bwd_prep(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots,
                             const uint8_t* set_id, int32_t dur_off, int32_t vocab_padded, int32_t d,
                             const float* chord, int64_t ldc, const float* g, int64_t ldg, int32_t dtype, void* onehot,

@@ -72,6 +72,7 @@ SIGNATURES = {
     "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
                                       POINTER(GroupsStruct), c_int32, _P]),
     "pb_rgcn_gemm_bwd_weight_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "pb_rgcn_gemm_bwd_weight_workspace_bytes_for": (c_size_t, [c_int64, c_int32, c_int32, c_int32]),
     "pb_rgcn_gemm_bwd_weight": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int32, c_int32,
                                         POINTER(GroupsStruct), c_int32, _P, c_size_t, _P]),
     "pb_gemm_f32_check": (c_int, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32,
@@ -96,6 +97,7 @@ SIGNATURES = {
     "pb_ce_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
     "pb_ce_rows_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "pb_ce_rows_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "pb_token_hist": (c_int, [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
     "pb_dataset_structure": (c_int, [_P, c_int64, c_int32, _P, _P]),
     "pb_dataset_tokens": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P]),
     "pb_mtp_from_logits": (c_int, [_P, c_int64, c_int32, _P, _P, c_int64, c_int32, c_int32, c_int32, c_int32, _P, _P]),

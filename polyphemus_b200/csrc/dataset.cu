@@ -123,3 +123,49 @@ extern "C" int pb_mtp_from_logits(const void* c_logits, int64_t ld_node, int32_t
   PB_LAUNCH_CHECK();
   return PB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------- token histograms
+// Token counts per table set for the BatchNorm statistics of the folded chord embedding (vae.ContentEncoder._bn_table:
+// BatchNorm over Linear(one_hot) rows == histogram-weighted statistics of the table rows, model.py:355-376).
+// counts i64 [2][n_pitch + n_dur]: set 0 = non-drum nodes, set 1 = drum nodes; pitch bins first, duration bins after.
+// Shared-memory histogram per CTA, integer atomics (exact, order-independent), no host read-back.
+namespace pb {
+__global__ void __launch_bounds__(256) token_hist_kernel(const int16_t* __restrict__ tokens, int64_t tok_stride,
+                                                         int tok_offset, int n_slots, const uint8_t* __restrict__ set_id,
+                                                         int64_t n_nodes, int n_pitch, int n_dur,
+                                                         unsigned long long* __restrict__ counts) {
+  extern __shared__ unsigned int hist[];                 // [2][n_pitch + n_dur]
+  const int bins = n_pitch + n_dur;
+  for (int i = threadIdx.x; i < 2 * bins; i += blockDim.x) hist[i] = 0u;
+  __syncthreads();
+  const int64_t total = n_nodes * n_slots;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / n_slots;
+    const int t = (int)(i - v * n_slots);
+    const int16_t* tk = tokens + v * tok_stride + tok_offset + 2 * t;
+    const int p = tk[0], du = tk[1];
+    unsigned int* h = hist + (set_id[v] ? bins : 0);
+    if (p >= 0 && p < n_pitch) atomicAdd(h + p, 1u);
+    if (du >= 0 && du < n_dur) atomicAdd(h + n_pitch + du, 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * bins; i += blockDim.x)
+    if (hist[i]) atomicAdd(counts + i, (unsigned long long)hist[i]);
+}
+}  // namespace pb
+
+extern "C" int pb_token_hist(const int16_t* tokens, int64_t tok_stride, int32_t tok_offset, int32_t n_slots,
+                             const uint8_t* set_id, int64_t n_nodes, int32_t n_pitch, int32_t n_dur, int64_t* counts,
+                             pb_stream_t stream) {
+  PB_REQUIRE(tokens && set_id && counts && n_nodes >= 0 && n_slots > 0 && n_pitch > 0 && n_dur > 0, "pb_token_hist: bad arguments");
+  const int bins = n_pitch + n_dur;
+  cudaStream_t st = as_stream(stream);
+  PB_CUDA(cudaMemsetAsync(counts, 0, (size_t)2 * bins * sizeof(int64_t), st));
+  if (n_nodes == 0) return PB_OK;
+  const int64_t total = n_nodes * n_slots;
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 4);
+  pb::token_hist_kernel<<<grid, 256, (size_t)2 * bins * sizeof(unsigned int), st>>>(
+      tokens, tok_stride, tok_offset, n_slots, set_id, n_nodes, n_pitch, n_dur, reinterpret_cast<unsigned long long*>(counts));
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}

@@ -629,13 +629,23 @@ extern "C" int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t
 
 static inline int64_t pad4(int64_t v) { return (v + 3) / 4 * 4; }
 
-extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k) {
-  if (m <= 0 || d <= 0 || k <= 0) return 0;
+// split-K partials, plus (PB_F32 only) the K-major transposed operand copies
+static size_t bwd_weight_ws(int64_t m, int32_t d, int32_t k, bool need_transposed) {
   const int s = std::max(bwd_weight_splits(m, d, k, true), bwd_weight_splits(m, d, k, false)) + 4;  // +4: per-group minimum
   const size_t partials = align_up((size_t)s * k * d * sizeof(float), 256);
   const size_t transposed = 2 * (align_up((size_t)k * pad4(m) * sizeof(float), 256) +
-                                 align_up((size_t)d * pad4(m) * sizeof(float), 256));   // PB_F32 only
-  return partials + transposed;
+                                 align_up((size_t)d * pad4(m) * sizeof(float), 256));
+  return partials + (need_transposed ? transposed : 0);
+}
+
+extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes(int64_t m, int32_t d, int32_t k) {
+  if (m <= 0 || d <= 0 || k <= 0) return 0;
+  return bwd_weight_ws(m, d, k, true);
+}
+
+extern "C" size_t pb_rgcn_gemm_bwd_weight_workspace_bytes_for(int64_t m, int32_t d, int32_t k, int32_t dtype) {
+  if (m <= 0 || d <= 0 || k <= 0) return 0;
+  return bwd_weight_ws(m, d, k, dtype != PB_BF16);
 }
 
 extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64_t lda, const void* g_hi,
@@ -648,7 +658,7 @@ extern "C" int pb_rgcn_gemm_bwd_weight(const void* a_hi, const void* a_lo, int64
   PB_REQUIRE(a_hi && g_hi && d_wcat && workspace, "pb_rgcn_gemm_bwd_weight: null pointer");
   PB_REQUIRE(dtype == PB_BF16 || (a_lo && g_lo), "pb_rgcn_gemm_bwd_weight: PB_F32 needs lo operands");
   PB_REQUIRE(lda >= k && lda % 8 == 0 && ldg >= d && ldg % 8 == 0, "pb_rgcn_gemm_bwd_weight: bad leading dimension");
-  PB_REQUIRE(workspace_bytes >= pb_rgcn_gemm_bwd_weight_workspace_bytes(m, d, k), "pb_rgcn_gemm_bwd_weight: workspace too small");
+  PB_REQUIRE(workspace_bytes >= pb_rgcn_gemm_bwd_weight_workspace_bytes_for(m, d, k, dtype), "pb_rgcn_gemm_bwd_weight: workspace too small");
   const bool bf16 = dtype == PB_BF16;
   int splits = bwd_weight_splits(m, d, k, bf16);
   cudaStream_t st = as_stream(stream);

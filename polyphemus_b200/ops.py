@@ -252,7 +252,7 @@ class RGCLayerFn(torch.autograd.Function):
             # structured layout: one split-K launch whose splits follow the row groups + a grouped reduce that sums
             # the track block per group (weight[0..3]) and the onset / next / root blocks over all rows
             d_wcat = torch.empty((kw, d), dtype=torch.float32, device=dev)
-            wws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, d, k)
+            wws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(n, d, k, cfg.dtype)
             wws = torch.empty(wws_bytes, dtype=torch.uint8, device=dev)
             _call("pb_rgcn_gemm_bwd_weight", a_hi.data_ptr(), _ffi.ptr(a_lo), k, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
                   d_wcat.data_ptr(), n, d, k, groups, cfg.dtype, wws.data_ptr(), wws_bytes, st)
@@ -361,7 +361,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
             dw = None
             if ctx.needs_input_grad[1]:
                 dw = torch.empty((n, k), dtype=torch.float32, device=dev)
-                ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(m, k, n)
+                ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(m, k, n, dtype)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 # dW[n, k] = g^T @ x: the split-K kernel contracts over the rows of its two [m, .] operands
                 _call("pb_rgcn_gemm_bwd_weight", g_hi.data_ptr(), _ffi.ptr(g_lo), n, x_hi.data_ptr(), _ffi.ptr(x_lo), k,
@@ -397,7 +397,7 @@ class TableGatherFn(torch.autograd.Function):
         oh_lo = None if dtype == _ffi.PB_BF16 else torch.zeros_like(onehot)     # 0/1 is exact in TF32
         lib = _ffi.lib()
         d_table = torch.empty((vp, c), dtype=torch.float32, device=dev)
-        ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(m, c, vp)
+        ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(m, c, vp, dtype)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _call("pb_rgcn_gemm_bwd_weight", onehot.data_ptr(), _ffi.ptr(oh_lo), vp, g_hi.data_ptr(), _ffi.ptr(g_lo), c,
@@ -560,7 +560,7 @@ class ChordEmbedFn(torch.autograd.Function):
         gcat_lo = None if bf16 else torch.empty((n, 2 * d), dtype=op_dtype, device=dev)
         d_t = torch.empty((kk, 2 * d), dtype=torch.float32, device=dev)
         lib = _ffi.lib()
-        ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes(n, 2 * d, kk)
+        ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(n, 2 * d, kk, dtype)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = _ffi.stream()

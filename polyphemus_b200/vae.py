@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import _ffi, ops
 from .conv import GCN, _reset
 from .graph import Graph, graphs_from_tensor
 
@@ -272,11 +272,15 @@ class ContentEncoder(nn.Module):
         with torch.autocast(device_type=tokens.device.type, enabled=False):
             counts = (None, None)
             if self.training:
-                ids = tokens[:, 1:, :].long()
-                sets = is_drum.long().view(-1, 1)
-                cnt_p = torch.bincount((ids[..., 0] + N_PITCH_TOKENS * sets).reshape(-1), minlength=2 * N_PITCH_TOKENS)
-                cnt_d = torch.bincount((ids[..., 1] + N_DUR_TOKENS * sets).reshape(-1), minlength=2 * N_DUR_TOKENS)
-                counts = (cnt_p.view(2, -1), cnt_d.view(2, -1))
+                # token histograms per table set in one kernel (torch.bincount reads the maximum back to the host: a
+                # full device sync in the middle of the forward pass)
+                both = torch.empty((2, N_PITCH_TOKENS + N_DUR_TOKENS), dtype=torch.int64, device=tokens.device)
+                flags = is_drum.view(torch.uint8) if is_drum.dtype == torch.bool else is_drum
+                with torch.cuda.device(tokens.device):
+                    _ffi.call("pb_token_hist", tokens.data_ptr(), tokens.stride(0), 2, t, flags.data_ptr(), tokens.size(0),
+                              N_PITCH_TOKENS, N_DUR_TOKENS, both.data_ptr(), _ffi.stream())
+                cnt_p, cnt_d = both[:, :N_PITCH_TOKENS], both[:, N_PITCH_TOKENS:]
+                counts = (cnt_p, cnt_d)
             if self.training and all(bn.track_running_stats and bn.momentum is not None
                                      for bn in (self.bn_drums, self.bn_non_drums, self.bn_dur)):
                 p_tabs, d_tabs = self._bn_tables_batched(*counts)                  # [2, 131, c], [2, 99, c]

@@ -173,3 +173,29 @@ def test_graph_build_is_deterministic(cuda):
     g2, _ = _build(s_np, cuda)
     assert torch.equal(g1.edge_index, g2.edge_index) and torch.equal(g1.plan.in_eid, g2.plan.in_eid)
     assert torch.equal(g1.plan.out_rec, g2.plan.out_rec)
+
+
+def test_integration_md_snippet_runs(cuda, built_lib):
+    """INTEGRATION.md §2 is the binding a maintainer would copy: execute it verbatim and check it against the oracle."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```python\n(.*?)```", text, re.S) if "[integration-snippet]" in b]
+    assert len(blocks) == 1
+    s_np = go.synthetic_structure(5, 3, 0.3, seed=4)
+    s_np[2, 1] = False                                        # an empty bar
+    env = {"LIB": built_lib, "s_tensor": torch.from_numpy(s_np.copy())}
+    exec(compile(blocks[0], "INTEGRATION.md", "exec"), env)
+    arrays = go.batch_graph(s_np)
+    assert env["N"] == arrays.num_nodes and env["E"] == arrays.edge_index.shape[1]
+    np.testing.assert_array_equal(env["edge_index"].cpu().numpy(), arrays.edge_index)
+    np.testing.assert_array_equal(env["edge_type"].cpu().numpy(), arrays.edge_type)
+    np.testing.assert_array_equal(env["edge_dist"].cpu().numpy(), arrays.edge_dist)
+    np.testing.assert_array_equal(env["node_features"].cpu().numpy(), arrays.node_features)
+    np.testing.assert_array_equal(env["bars"].cpu().numpy(), arrays.bars)
+    ea = env["edge_attrs"].cpu().numpy()
+    np.testing.assert_array_equal(ea[:, 0], arrays.edge_type.astype(np.float32))
+    np.testing.assert_array_equal(ea[:, 1:].argmax(1), arrays.edge_dist)
+    assert env["totals"].numel() == 8

@@ -706,3 +706,20 @@ def test_bar_expand_and_segment_sum(cuda, d):
     x.backward(g_x.to(cuda))
     ref = torch.zeros(29, d, dtype=torch.float64).index_add_(0, seg, g_x.double())
     torch.testing.assert_close(z_dev.grad.cpu().double(), ref, rtol=1e-5, atol=1e-5)
+
+
+def test_token_hist_matches_bincount(cuda):
+    """pb_token_hist == per-set bincount of the (pitch, duration) ids of slots 1..15 (the histogram that weights the
+    BatchNorm statistics of the folded embedding tables, model.py:355-376), incl. a batch without drum nodes."""
+    from polyphemus_b200.train import synthetic_tokens
+    ffi = _ffi()
+    for n, drum_frac in ((5000, 0.3), (777, 0.0), (1, 1.0)):
+        tokens = synthetic_tokens(n, torch.Generator().manual_seed(n)).to(cuda)
+        is_drum = (torch.rand(n, generator=torch.Generator().manual_seed(n + 1)) < drum_frac).to(cuda)
+        counts = torch.full((2, 230), -1, dtype=torch.int64, device=cuda)
+        ffi.check(ffi.lib().pb_token_hist(ptr(tokens), 32, 2, 15, ptr(is_drum.view(torch.uint8)), n, 131, 99, ptr(counts), st()), "hist")
+        ids = tokens[:, 1:, :].long().cpu()
+        for s_ in (0, 1):
+            sel = ids[is_drum.cpu() == bool(s_)]
+            want = torch.cat((torch.bincount(sel[..., 0].reshape(-1), minlength=131), torch.bincount(sel[..., 1].reshape(-1), minlength=99)))
+            assert torch.equal(counts[s_].cpu(), want)
