@@ -273,7 +273,8 @@ int pb_bn_relu_res_fwd(const void* out, int64_t ldo, const void* x_res, const fl
                        int32_t act_dtype, pb_stream_t stream);
 /* Backward of y = x + relu(bn(out)) wrt out (training statistics):
  *   g_out f32 [m,d] (+ GEMM-operand copies g_hi/g_lo in `dtype`), g_gamma, g_beta, g_bias(=colsum g_out).
- *   The residual branch gradient is gy itself (consumed by pb_agg_bwd as gy_res). */
+ *   The residual branch gradient is gy itself (consumed by pb_agg_bwd as gy_res). With row groups the padding rows of
+ *   g_hi / g_lo are written as zero (the weight-gradient GEMM contracts over all m rows). */
 int pb_bn_relu_res_bwd(const void* gy, const void* out, int64_t ldo, const float* gamma,
                        const float* save_mean_rstd, const float* bn_coef, int64_t m, int32_t d,
                        const pb_groups_t* groups, int32_t dtype, void* g_hi, void* g_lo, int64_t ldg, float* g_gamma,

@@ -224,7 +224,8 @@ class RGCLayerFn(torch.autograd.Function):
         groups = None if struct is None else struct.groups_ref()
         with torch.cuda.device(dev):
             st = _ffi.stream()
-            g_hi, g_lo = _operand(n, d, cfg.dtype, dev, zero=struct is not None)   # padding rows must stay zero
+            # padding rows of the structured layout must be zero: pb_bn_relu_res_bwd writes them itself
+            g_hi, g_lo = _operand(n, d, cfg.dtype, dev, zero=struct is not None and not cfg.batch_norm)
             g_bias = torch.empty(d, dtype=torch.float32, device=dev)
             ws_bytes = lib.pb_bn_workspace_bytes(n, d)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
