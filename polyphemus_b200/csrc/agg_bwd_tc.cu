@@ -14,8 +14,11 @@
 // and the [d, 32] fp32 accumulator never leaves TMEM until the CTA is done. No atomics: an edge's stage slot is its
 // position in the CTA's (visit-ordered) edge range, so the summation order is fixed -> bit-reproducible.
 //
-// One persistent CTA per SM: 16 gather warps + 1 MMA warp + 1 L2-prefetch warp (measured: 16 / 20 / 24 gather warps
-// give 381 / 391 / 398 us on the LMD16 batch-256 graph — the kernel is bound by instruction issue, not by occupancy). Shared memory: the edge table T [32, d] fp32 (read per
+// One persistent CTA per SM: 14 gather warps (128 registers each, no spills: with the 214 KB shared-memory carve-out L1 is
+// ~14 KB and every spilled word is an L2 round trip — 16 / 24 warps measure 400 / 460 us against 340) + 1 MMA warp + 1
+// L2-prefetch warp. Decomposition measured on the LMD16 batch-256 graph (d = 512): gather + math alone 316 us, staging +
+// barriers + MMA +22 us, removing the row loads entirely changes nothing: the kernel is bound by the ~300 instructions a
+// warp spends per edge (16 channels per lane) at ~0.5 IPC per scheduler, not by HBM. Shared memory: the edge table T [32, d] fp32 (read per
 // edge by every lane), 4 stages x 32 edges of Q (4 x 32 KB at d = 512) and their one-hot lines (4 x 4 KB).
 #include "common.cuh"
 #include "mbar.cuh"
@@ -27,13 +30,20 @@ namespace pb {
 #define PB_TC_SLEEP 256
 #endif
 #ifndef PB_TC_WARPS
-#define PB_TC_WARPS 16
+#define PB_TC_WARPS 14
 #endif
 constexpr int kTcProducers = PB_TC_WARPS;              // gather warps per CTA
 constexpr int kTcThreads = (kTcProducers + 2) * 32;    // + the MMA warp + the L2 prefetch warp
-constexpr int kTcAhead = 64;                           // sources the prefetch warp may run ahead of the finished ones
-constexpr int kTcStages = 4;
-constexpr int kTcStageEdges = 32;                      // K extent of a stage: two k-steps of 16
+#ifndef PB_TC_AHEAD
+#define PB_TC_AHEAD 64
+#endif
+constexpr int kTcAhead = PB_TC_AHEAD;                           // sources the prefetch warp may run ahead of the finished ones
+#ifndef PB_TC_STAGES
+#define PB_TC_STAGES 4
+#define PB_TC_STAGE_EDGES 32
+#endif
+constexpr int kTcStages = PB_TC_STAGES;
+constexpr int kTcStageEdges = PB_TC_STAGE_EDGES;       // K extent of a stage: k-steps of 16
 constexpr int kTcN = 64;                               // 32 distances padded to one 128-byte MN-major line
 constexpr int kTcBStage = kTcStageEdges * 128;         // one-hot lines of a stage (bytes)
 
@@ -84,7 +94,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
   // sign masks of the table in the lanes' channel order: word [dist][lane] = (bits of T > 0) | (bits of T < 0) << 16,
   // bit 4 j + i <-> channel 4 (lane + 32 j) + i  (the order of the lane's keep-bit word)
   uint32_t* t_sign = reinterpret_cast<uint32_t*>(t_s + PB_N_DISTS * d);  // [32][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(t_sign + PB_N_DISTS * 32);
+  uint2* mask_lut = reinterpret_cast<uint2*>(t_sign + PB_N_DISTS * 32);   // [16]: 4 keep bits -> bf16-pair AND masks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mask_lut + 16);
   uint64_t* full = bars;                       // [kTcStages], one arrival per edge slot
   uint64_t* empty = bars + kTcStages;          // [kTcStages], tcgen05.commit
   uint64_t* done = bars + 2 * kTcStages;
@@ -124,6 +135,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
       neg |= ((t.x < 0.f) | ((t.y < 0.f) << 1) | ((t.z < 0.f) << 2) | ((t.w < 0.f) << 3)) << (4 * j);
     }
     t_sign[i] = pos | (neg << 16);
+  }
+  if (threadIdx.x < 16) {
+    const uint32_t b = threadIdx.x;
+    mask_lut[b] = make_uint2(((b & 1u) ? 0xFFFFu : 0u) | ((b & 2u) ? 0xFFFF0000u : 0u),
+                             ((b & 4u) ? 0xFFFFu : 0u) | ((b & 8u) ? 0xFFFF0000u : 0u));
   }
   fence_proxy_async();
   tc_fence_before();
@@ -166,23 +182,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
         prefetch_l2_bulk(static_cast<const char*>(x) + (size_t)m.x * kRowA, kRowA);
         if (gy_res) prefetch_l2_bulk(static_cast<const char*>(gy_res) + (size_t)m.x * kRowA, kRowA);
         prefetch_l2_bulk(d_a + (size_t)m.x * ldda + (size_t)n_rel * d, kRowG);
-        for (int s = 0; s < m.z; ++s) {
-          const int4 r = __ldg(out_rec + m.y + s);
-          prefetch_l2_bulk(d_a + (size_t)r.x * ldda + (size_t)(r.y & 0xff) * d, kRowG);
-          if constexpr (DROPOUT) prefetch_l2_bulk(keep_bits + (size_t)(uint32_t)r.z * G16 * 32, G16 * 64);
+        // all records of the source first (independent loads, one round trip), then the prefetches they address
+        int4 r[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) r[s] = s < m.z ? __ldg(out_rec + m.y + s) : make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          if (s < m.z) {
+            prefetch_l2_bulk(d_a + (size_t)r[s].x * ldda + (size_t)(r[s].y & 0xff) * d, kRowG);
+            if constexpr (DROPOUT) prefetch_l2_bulk(keep_bits + (size_t)(uint32_t)r[s].z * G16 * 32, G16 * 64);
+          }
+        }
+        for (int s = 8; s < m.z; ++s) {
+          const int4 q = __ldg(out_rec + m.y + s);
+          prefetch_l2_bulk(d_a + (size_t)q.x * ldda + (size_t)(q.y & 0xff) * d, kRowG);
+          if constexpr (DROPOUT) prefetch_l2_bulk(keep_bits + (size_t)(uint32_t)q.z * G16 * 32, G16 * 64);
         }
       }
     }
   } else {
     // ================================================================== gather warps (one source at a time)
     const int last_pos = n_edges - 1;
+    int stage_ok = -1;                                             // last stage (p / 32) whose buffer is known to be free
+    // per-lane constants of the Q-row layout: channel chunk c4 = lane + 32 j lives in 64-channel block c4 / 16, 16-byte
+    // unit (c4 % 16) / 2 of the edge's 128-byte line (units XOR-swizzled with the line index), half (c4 & 1)
+    uint32_t q_off[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c4 = lane + 32 * j;
+      q_off[j] = (uint32_t)(c4 >> 4) * kChunkBytes + (uint32_t)(((c4 & 15) >> 1) << 4) + (uint32_t)(c4 & 1) * 8u;
+    }
+    const uint32_t b_off = (uint32_t)((lane >> 2) << 4) + (uint32_t)(lane & 3) * 4u;
+    struct EdgeRegs { uint2 raw[CPL]; uint32_t kw; int meta, cnt; };
+    // The dependent chain of a source is  {row, first edge, degree} -> edge records -> rows.  Its first two links are
+    // taken off the critical path by running them ahead: the metadata of the source after next and the records of the
+    // next source are loaded while the current one is processed, so a source starts by issuing ALL its first loads
+    // (features, residual, root block, the rows of its first three edges) at once — one memory round trip instead of
+    // three.
+    auto load_meta = [&](int64_t vi, int4& m, int& vep) {
+      if (vi < r1) { m = __ldg(visit_meta + vi); vep = __ldg(visit_edge_ptr + vi); } else { m = make_int4(0, 0, 0, 0); vep = 0; }
+    };
+    auto load_rec = [&](const int4& m) {
+      return lane < m.z ? __ldg(out_rec + m.y + lane) : make_int4(0, 0, 0, 0);
+    };
+    int4 m_cur, m_nxt, m_nn, rec_cur, rec_nxt;
+    int vep_cur, vep_nxt, vep_nn;
+    load_meta(r0 + warp, m_cur, vep_cur);
+    load_meta(r0 + warp + kTcProducers, m_nxt, vep_nxt);
+    rec_cur = load_rec(m_cur);
     for (int64_t vi = r0 + warp; vi < r1; vi += kTcProducers) {
-      const int4 m = __ldg(visit_meta + vi);                       // {row, first out-edge, out-degree, -}
-      const int u = m.x, beg = m.y, end = m.y + m.z;
-      const int pos0 = __ldg(visit_edge_ptr + vi) - e0 - beg;      // position of out-edge i in the CTA's range: pos0 + i
+      load_meta(vi + 2 * kTcProducers, m_nn, vep_nn);             // two sources ahead
+      rec_nxt = load_rec(m_nxt);                                  // one source ahead (its metadata arrived a source ago)
+      const int u = m_cur.x, beg = m_cur.y, end = m_cur.y + m_cur.z;
+      const int pos0 = vep_cur - e0 - beg;                        // position of out-edge i in the CTA's range: pos0 + i
       int base = beg;
-      int4 my_rec = base + lane < end ? __ldg(out_rec + base + lane) : make_int4(0, 0, 0, 0);
+      int4 my_rec = rec_cur;
       float4 xu[CPL], acc[CPL];
+      // 1[x * T > 0] = (x > 0 and T > 0) or (x < 0 and T < 0): sign bits of this source's features, once per source
+      uint32_t xpos = 0, xneg = 0;
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
         const size_t c4 = 4 * (size_t)(lane + 32 * j);
@@ -194,93 +251,73 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
           const float4 r = act_ld4_stream<ABF>(gy_res, (size_t)u * d + c4);                                         // residual branch
           acc[j].x += r.x; acc[j].y += r.y; acc[j].z += r.z; acc[j].w += r.w;
         }
-      }
-      // 1[x * T > 0] = (x > 0 and T > 0) or (x < 0 and T < 0): sign bits of this source's features, once per source
-      uint32_t xpos = 0, xneg = 0;
-#pragma unroll
-      for (int j = 0; j < CPL; ++j) {
-        xpos |= ((xu[j].x > 0.f) | ((xu[j].y > 0.f) << 1) | ((xu[j].z > 0.f) << 2) | ((xu[j].w > 0.f) << 3)) << (4 * j);
-        xneg |= ((xu[j].x < 0.f) | ((xu[j].y < 0.f) << 1) | ((xu[j].z < 0.f) << 2) | ((xu[j].w < 0.f) << 3)) << (4 * j);
+        // integer view: v > 0 <=> bits in (0, 0x7f800000]; v < 0 <=> bits as unsigned > 0x80000000 (NaN never occurs)
+        const int bx = __float_as_int(xu[j].x), by = __float_as_int(xu[j].y), bz = __float_as_int(xu[j].z), bw = __float_as_int(xu[j].w);
+        xpos |= (uint32_t)((bx > 0) | ((by > 0) << 1) | ((bz > 0) << 2) | ((bw > 0) << 3)) << (4 * j);
+        xneg |= (uint32_t)(((uint32_t)bx > 0x80000000u) | (((uint32_t)by > 0x80000000u) << 1) | (((uint32_t)bz > 0x80000000u) << 2) |
+                           (((uint32_t)bw > 0x80000000u) << 3)) << (4 * j);
       }
       // software pipeline over the out-edges: the gradient row and keep-bits of edge i+1 are in flight while edge i
-      // is consumed
-      uint2 nraw[CPL];
-      uint32_t nkw[G16];
-      int nmeta = 0, ncnt = 0;
-      auto fetch = [&](int i) {
+      // is consumed (two register sets, used alternately: no copies)
+      auto fetch = [&](EdgeRegs& e, int i) {
         if (i - base == 32) {  // warp-uniform (out-degree > 32 only)
           base = i;
           my_rec = base + lane < end ? __ldg(out_rec + base + lane) : make_int4(0, 0, 0, 0);
         }
         const int dst = __shfl_sync(kFull, my_rec.x, i - base);
-        nmeta = __shfl_sync(kFull, my_rec.y, i - base);
-        ncnt = __shfl_sync(kFull, my_rec.w, i - base);
-        const __nv_bfloat16* grow = d_a + (size_t)dst * ldda + (size_t)(nmeta & 0xff) * d + 4 * lane;
+        e.meta = __shfl_sync(kFull, my_rec.y, i - base);
+        e.cnt = __shfl_sync(kFull, my_rec.w, i - base);
+        const __nv_bfloat16* grow = d_a + (size_t)dst * ldda + (size_t)(e.meta & 0xff) * d + 4 * lane;
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) nraw[j] = __ldg(reinterpret_cast<const uint2*>(grow + 128 * j));
+        for (int j = 0; j < CPL; ++j) e.raw[j] = __ldg(reinterpret_cast<const uint2*>(grow + 128 * j));
         if constexpr (DROPOUT) {
           const uint32_t eid = (uint32_t)__shfl_sync(kFull, my_rec.z, i - base);
-#pragma unroll
-          for (int q = 0; q < G16; ++q) nkw[q] = __ldg(keep_bits + ((size_t)eid * G16 + q) * 32 + lane);
+          e.kw = __ldg(keep_bits + (size_t)eid * G16 * 32 + lane);
         }
       };
-      if (beg < end) fetch(beg);
       int pend_n = 0;                                             // slots written but not yet published (one stage)
-      for (int i = beg; i < end; ++i) {
-        uint2 raw[CPL];
-        uint32_t kw[G16];
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) raw[j] = nraw[j];
-#pragma unroll
-        for (int q = 0; q < G16; ++q) kw[q] = nkw[q];
-        const int meta = nmeta, cnt = ncnt;
-        if (i + 1 < end) fetch(i + 1);
-        const int dist = (meta >> 8) & (PB_N_DISTS - 1);
+      auto process = [&](const EdgeRegs& e, int i) {
+        const int dist = (e.meta >> 8) & (PB_N_DISTS - 1);
         const float* trow = t_s + dist * d + 4 * lane;
-        float coef = cnt > 1 ? 1.0f / (float)cnt : 1.0f;            // d(mean)/d(sum), one reciprocal per edge
+        float coef = e.cnt > 1 ? 1.0f / (float)e.cnt : 1.0f;      // d(mean)/d(sum), one reciprocal per edge
         if constexpr (DROPOUT) coef *= keep_scale;
         // stage slot of this edge: its position in the CTA's edge range
         const int p = pos0 + i;
-        const int st = (p / kTcStageEdges) & (kTcStages - 1), slot = p & (kTcStageEdges - 1);
-        mbar_wait_backoff(empty + st, (uint32_t)(((p / (kTcStageEdges * kTcStages)) & 1) ^ 1));
+        const int sidx = p / kTcStageEdges, st = sidx & (kTcStages - 1), slot = p & (kTcStageEdges - 1);
+        if (sidx != stage_ok) {                                    // warp-uniform: first slot this warp writes in the stage
+          mbar_wait_backoff(empty + st, (uint32_t)(((sidx / kTcStages) & 1) ^ 1));
+          stage_ok = sidx;
+        }
+        const uint32_t swz = (uint32_t)(slot & 7) << 4;
         const uint32_t q_row = q_u32 + st * kQStage + slot * 128;
         // keep decision of the lane's 16 channels as one bit mask (dropout bit and 1[x * T > 0]), applied to the packed
         // bf16 gradient words before they are unpacked: a dropped channel is an exact +0 in everything that follows
         const uint32_t ts = t_sign[dist * 32 + lane];
         uint32_t keep = (xpos & ts) | (xneg & (ts >> 16));
-        if constexpr (DROPOUT) keep &= kw[0];
-        const uint32_t swz = (uint32_t)(slot & 7) << 4;
+        if constexpr (DROPOUT) keep &= e.kw;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-          const uint32_t b = keep >> (4 * j);
-          // bits (b0, b1) -> 0xFFFF fields: (b0 | b1 << 16) * 0xFFFF
-          const uint32_t m0 = ((b & 1u) | ((b & 2u) << 15)) * 0xFFFFu, m1 = (((b >> 2) & 1u) | ((b & 8u) << 13)) * 0xFFFFu;
-          const float2 da = unpack_bf16x2(raw[j].x & m0), db = unpack_bf16x2(raw[j].y & m1);
+          const uint2 mk = mask_lut[(keep >> (4 * j)) & 15u];       // 4 keep bits -> two words of 0xFFFF fields
+          const float2 da = unpack_bf16x2(e.raw[j].x & mk.x), db = unpack_bf16x2(e.raw[j].y & mk.y);
           const float4 ds = make_float4(da.x * coef, da.y * coef, db.x * coef, db.y * coef);
           const float4 t = *reinterpret_cast<const float4*>(trow + 128 * j);
           const float4 xv = xu[j];
           acc[j].x += ds.x * t.x; acc[j].y += ds.y * t.y; acc[j].z += ds.z * t.z; acc[j].w += ds.w * t.w;
-          // q_e (bf16) -> MN-major operand: channel chunk c4 = lane + 32 j lives in 64-channel block c4 / 16, 16-byte
-          // unit (c4 % 16) / 2 of the edge's 128-byte line, units XOR-swizzled with the line index
-          const int c4 = lane + 32 * j;
-          const uint32_t addr = q_row + (uint32_t)(c4 >> 4) * kChunkBytes + ((uint32_t)(((c4 & 15) >> 1) << 4) ^ swz) +
-                                (uint32_t)(c4 & 1) * 8u;
-          sts64(addr, pack_bf16x2(ds.x * xv.x, ds.y * xv.y), pack_bf16x2(ds.z * xv.z, ds.w * xv.w));
+          sts64(q_row + (q_off[j] ^ swz), pack_bf16x2(ds.x * xv.x, ds.y * xv.y), pack_bf16x2(ds.z * xv.z, ds.w * xv.w));
         }
         // one-hot line of the distance: elements n = 2 lane, 2 lane + 1 (lanes >= 16 would write n >= 32: always zero)
         if (lane < 16) {
           const uint32_t v = (dist == 2 * lane ? 0x3F80u : 0u) | (dist == 2 * lane + 1 ? 0x3F800000u : 0u);
-          sts32(b_u32 + st * kTcBStage + slot * 128 + (uint32_t)(((lane >> 2) ^ (slot & 7)) << 4) + (uint32_t)(lane & 3) * 4u, v);
+          sts32(b_u32 + st * kTcBStage + slot * 128 + (b_off ^ swz), v);
         }
-        // publish: the proxy fence is the expensive part (it orders this warp's generic-proxy stores against the tensor
-        // core's async-proxy reads), so the slots a source fills in one stage are published together
+        // publish: the proxy fence orders this warp's generic-proxy stores against the tensor core's async-proxy reads;
+        // the slots a source fills in one stage are published together
         ++pend_n;
         const bool tail = p == last_pos && slot != kTcStageEdges - 1;         // the CTA's last, partial stage
         if (i + 1 == end || slot == kTcStageEdges - 1 || tail) {              // warp-uniform
           if (tail) {
             for (int k = slot + 1; k < kTcStageEdges; ++k)
-              if (lane < 16)
-                sts32(b_u32 + st * kTcBStage + k * 128 + (uint32_t)(((lane >> 2) ^ (k & 7)) << 4) + (uint32_t)(lane & 3) * 4u, 0u);
+              if (lane < 16) sts32(b_u32 + st * kTcBStage + k * 128 + (b_off ^ ((uint32_t)(k & 7) << 4)), 0u);
             pend_n += kTcStageEdges - 1 - slot;
           }
           fence_proxy_async();
@@ -288,10 +325,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
           if (lane == 0) mbar_arrive_n(full + st, (uint32_t)pend_n);
           pend_n = 0;
         }
+      };
+      EdgeRegs ea, eb, ec;                                        // three rows in flight
+      if (beg < end) fetch(ea, beg);
+      if (beg + 1 < end) fetch(eb, beg + 1);
+      for (int i = beg; i < end; i += 3) {
+        if (i + 2 < end) fetch(ec, i + 2);
+        process(ea, i);
+        if (i + 1 >= end) break;
+        if (i + 3 < end) fetch(ea, i + 3);
+        process(eb, i + 1);
+        if (i + 2 >= end) break;
+        if (i + 4 < end) fetch(eb, i + 4);
+        process(ec, i + 2);
       }
 #pragma unroll
       for (int j = 0; j < CPL; ++j) act_st4_stream<ABF>(gx, (size_t)u * d + 4 * (lane + 32 * j), acc[j]);
       if (lane == 0) atomicAdd(const_cast<int*>(progress), 1);
+      m_cur = m_nxt; vep_cur = vep_nxt; rec_cur = rec_nxt;
+      m_nxt = m_nn; vep_nxt = vep_nn;
     }
     // ================================================================== epilogue: TMEM -> partials [cta][32][d]
     if (warp < 4) {
@@ -325,7 +377,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
 
 static size_t tc_smem_bytes(int d) {
   return (size_t)kTcStages * ((size_t)(d / 64) * kTcStageEdges * 128 + kTcBStage) + (size_t)PB_N_DISTS * d * sizeof(float) +
-         PB_N_DISTS * 32 * sizeof(uint32_t) /*sign masks*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+         PB_N_DISTS * 32 * sizeof(uint32_t) /*sign masks*/ + 128 /*mask LUT*/ + 256 /*barriers*/ + 1024 /*alignment*/;
 }
 
 int agg_bwd_tc_ctas(int64_t n_nodes) {

@@ -55,8 +55,14 @@ static RowMap make_rowmap(const pb_groups_t* groups, int64_t m) {
 }
 static inline int64_t valid_rows(const RowMap& rm) { return rm.total; }
 
+#ifndef PB_BN_BWD_UNROLL
+#define PB_BN_BWD_UNROLL 1
+#endif
+#ifndef PB_BN_CTAS_PER_SM
+#define PB_BN_CTAS_PER_SM 4
+#endif
 constexpr int kColThreads = 256;
-constexpr int kColMaxCtas = 148 * 4;
+constexpr int kColMaxCtas = 148 * PB_BN_CTAS_PER_SM;
 
 static inline int col_ctas(int64_t m) {
   int64_t n = (m + 127) / 128;
@@ -239,7 +245,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const void*
                                                                     const float* __restrict__ mean_rstd,
                                                                     const RowMap rm, int d,
                                                                     float* __restrict__ partials) {
-  column_partials<2, 1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+  column_partials<2, PB_BN_BWD_UNROLL>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 g = act_ld4_stream<ABF>(gy, (size_t)r * d + 4 * c);
     const float4 o = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
@@ -286,7 +292,7 @@ __global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(
     const RowMap rm, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg,
     float* __restrict__ partials) {
   const float inv_m = 1.f / (float)rm.total;
-  column_partials<1, 1>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+  column_partials<1, PB_BN_BWD_UNROLL>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 g = act_ld4_stream<ABF>(gy, (size_t)r * d + 4 * c);
     const float4 o = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 mu = ldg4(coef + 4 * c), sc = ldg4(coef + d + 4 * c), be = ldg4(coef + 2 * d + 4 * c);
