@@ -55,11 +55,17 @@ static RowMap make_rowmap(const pb_groups_t* groups, int64_t m) {
 }
 static inline int64_t valid_rows(const RowMap& rm) { return rm.total; }
 
+// Row-loop unrolling of the column passes gives each thread several independent loads in flight, but only pays if the
+// registers still allow the 4 CTAs per SM the grid is sized for (592 CTAs = one wave): without the occupancy bound the
+// unrolled backward passes needed a second wave and got 30 % SLOWER (197 -> 258 us); with it 197 -> 174 us.
 #ifndef PB_BN_BWD_UNROLL
-#define PB_BN_BWD_UNROLL 1
+#define PB_BN_BWD_UNROLL 6
 #endif
 #ifndef PB_BN_CTAS_PER_SM
 #define PB_BN_CTAS_PER_SM 4
+#endif
+#ifndef PB_BN_MINB
+#define PB_BN_MINB 4
 #endif
 constexpr int kColThreads = 256;
 constexpr int kColMaxCtas = 148 * PB_BN_CTAS_PER_SM;
@@ -156,12 +162,22 @@ __device__ __forceinline__ bool finalize_sums(const float* __restrict__ partials
 }
 
 // ------------------------------------------------------------------------------------------------ forward stats
+#ifndef PB_BN_APPLY_UNROLL
+#define PB_BN_APPLY_UNROLL 2
+#endif
+#ifndef PB_BN_APPLY_CTAS
+#define PB_BN_APPLY_CTAS 32
+#endif
+constexpr int kApplyUnroll = PB_BN_APPLY_UNROLL;
+#ifndef PB_BN_STATS_UNROLL
+#define PB_BN_STATS_UNROLL 8
+#endif
 template <bool ABF>
-__global__ void __launch_bounds__(kColThreads) bn_stats_partial_kernel(const void* __restrict__ out, int64_t ldo,
+__global__ void __launch_bounds__(kColThreads, PB_BN_MINB) bn_stats_partial_kernel(const void* __restrict__ out, int64_t ldo,
                                                                       const RowMap rm, int d,
                                                                       float* __restrict__ partials) {
   const size_t shift_off = (size_t)rm.padded(0) * ldo;
-  column_partials<2, 4>(rm, d, partials, [&](int64_t r, int c, float4* v) {
+  column_partials<2, PB_BN_STATS_UNROLL>(rm, d, partials, [&](int64_t r, int c, float4* v) {
     const float4 x = act_ld4_stream<ABF>(out, (size_t)r * ldo + 4 * c);
     const float4 k = act_ld4<ABF>(out, shift_off + 4 * c);  // shift = first valid row (exact, cancels in the variance)
     const float4 dlt = make_float4(x.x - k.x, x.y - k.y, x.z - k.z, x.w - k.w);
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const void* __restrict__ 
                                                       void* __restrict__ y, int64_t m, int d, const RowMap rm) {
   const int nchunk = d >> 2;
   const int64_t total = m * nchunk;
-#pragma unroll 2
+#pragma unroll kApplyUnroll
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / nchunk;
     const int c = (int)(i - r * nchunk);
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const void* __restrict__ 
 // ------------------------------------------------------------------------------------------------ backward
 // pass 1: g_beta = sum gz, g_gamma = sum gz * xhat   with gz = gy * 1[(out-mean)*scale+beta > 0]
 template <bool ABF>
-__global__ void __launch_bounds__(kColThreads) bn_bwd_partial_kernel(const void* __restrict__ gy,
+__global__ void __launch_bounds__(kColThreads, PB_BN_MINB) bn_bwd_partial_kernel(const void* __restrict__ gy,
                                                                     const void* __restrict__ out, int64_t ldo,
                                                                     const float* __restrict__ coef,
                                                                     const float* __restrict__ mean_rstd,
@@ -286,7 +302,7 @@ __device__ __forceinline__ void store_g(void* g_hi, void* g_lo, size_t off, floa
 // pass 2: g_out = scale * (gz - g_beta/m - xhat * g_gamma/m), written as the GEMM operand; column sums of
 // g_out (the bias gradient of the layer feeding this BatchNorm) leave as partials.
 template <bool BF16, bool ABF>
-__global__ void __launch_bounds__(kColThreads) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(kColThreads, PB_BN_MINB) bn_bwd_apply_kernel(
     const void* __restrict__ gy, const void* __restrict__ out, int64_t ldo, const float* __restrict__ coef,
     const float* __restrict__ mean_rstd, const float* __restrict__ g_gamma, const float* __restrict__ g_beta,
     const RowMap rm, int d, void* __restrict__ g_hi, void* __restrict__ g_lo, int64_t ldg,
@@ -414,7 +430,7 @@ extern "C" int pb_bn_relu_res_fwd(const void* out, int64_t ldo, const void* x_re
   PB_REQUIRE(out && bn_coef && y, "pb_bn_relu_res_fwd: null pointer");
   PB_REQUIRE(ldo >= d && ldo % 4 == 0, "pb_bn_relu_res_fwd: bad ldo");
   const int64_t total = m * (d / 4);
-  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 32);
+  const unsigned grid = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * PB_BN_APPLY_CTAS);
   cudaStream_t st = as_stream(stream);
   const RowMap rm = make_rowmap(groups, m);
 #define PB_BN_APPLY(RELU, RES, ABF) \
