@@ -463,7 +463,7 @@ class BarPoolFn(torch.autograd.Function):
         n, d = h.shape
         n_bars = bar_ptr.numel() - 1
         h, gate = h.float().contiguous(), gate.float().contiguous().view(-1)
-        alpha = torch.empty(n, dtype=torch.float32, device=h.device)
+        alpha = torch.zeros(n, dtype=torch.float32, device=h.device)
         out = torch.empty((n_bars, d), dtype=torch.float32, device=h.device)
         with torch.cuda.device(h.device):
             _call("pb_bar_pool_fwd", h.data_ptr(), d, gate.data_ptr(), bar_ptr.data_ptr(), n_bars, d, alpha.data_ptr(),
@@ -515,9 +515,15 @@ def _check_bar_ptr(bar_ptr: torch.Tensor, n_bars: int) -> None:
         raise ValueError("bar_ptr must be a contiguous CUDA int32 tensor of n_bars + 1 node offsets")
 
 
+MAX_BAR_NODES = 128      # 4 tracks x 32 timesteps; pb_bar_pool_* keep a bar's scores in registers
+
+
 def bar_pool(h: torch.Tensor, gate: torch.Tensor, bar_ptr: torch.Tensor) -> torch.Tensor:
-    """Attention pooling of node rows h [N, d] per bar with scores gate [N]: f32 [n_bars, d]."""
+    """Attention pooling of node rows h [N, d] per bar with scores gate [N]: f32 [n_bars, d]. Segments longer than 128
+    nodes are not bars of this model: rejected by a device-side assertion (no host sync)."""
     _check_bar_ptr(bar_ptr, bar_ptr.numel() - 1)
+    if bar_ptr.numel() > 1:
+        torch._assert_async(((bar_ptr[1:] - bar_ptr[:-1]) <= MAX_BAR_NODES).all())
     return BarPoolFn.apply(h, gate.reshape(-1), bar_ptr)
 
 

@@ -5,7 +5,11 @@ file is the *caller* of that path and stays ordinary PyTorch. It keeps the refer
 (model.py:138-678): constructor kwargs (``VAE(**training.json["model"], device=...)``), forward signatures,
 module/attribute names and therefore state-dict keys (255 at the published config, checked against
 tests/golden/state_dict_keys.json), and the order in which parameters are created and re-initialised, so a
-given ``torch.manual_seed`` produces the reference's initial weights.
+given ``torch.manual_seed`` produces the initial weights of the reference run on the PyG stand-in (oracle/pyg_shim.py).
+Whether that equals a real torch-geometric 2.0.2 run depends on one recalled detail that cannot be checked here:
+``inits.reset`` is taken to recurse into ``gate_nn``'s MLP; if 2.0.2 only resets direct children, the gate MLP keeps its
+constructor draw and the random stream after it shifts. Trained checkpoints are unaffected (state-dict keys and shapes
+are what they load by).
 
 Differences from the reference are confined to *how* the same values are produced:
   * boolean-mask indexing (a host sync per mask, model.py:352-353,396-397,552-553,575-576) is replaced by
