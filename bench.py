@@ -209,6 +209,7 @@ def kernel_table(summary: dict, n: int, e: int, d: int, steps: int, precision: s
         "pb_bn_relu_res_fwd": ("hbm", 3 * n * d * ab),
         "pb_bn_relu_res_bwd": ("hbm", 4 * n * d * ab + n * d * s),
         "pb_rgcn_gemm_fwd": ("tensor", 2 * n_rows * k * d),          # executed flops (structured: 4d-wide operand)
+        "pb_rgcn_gemm_fwd_bn": ("tensor", 2 * n_rows * k * d),       # the same GEMM, BatchNorm column sums in its epilogue
         "pb_rgcn_gemm_bwd_data": ("tensor", 2 * n_rows * k * d),
         "pb_rgcn_gemm_bwd_weight": ("tensor", 2 * n_rows * k * d),
     }

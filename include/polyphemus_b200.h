@@ -225,6 +225,15 @@ int pb_weight_prep(const float* weight, const float* root, int32_t n_relations, 
 int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
                      const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
                      int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype, pb_stream_t stream);
+/* The same forward with the BatchNorm batch statistics as a by-product of the epilogue (model.py:202-203 without a second
+ * pass over `out`): bn_partials f32 [pb_rgcn_gemm_fwd_bn_partial_rows(m), 2, d] receives, per (128-row tile, 32-row
+ * quadrant), the column sums and sums of squares of the STORED output values over the real rows (the padding rows of a
+ * group are excluded). Zero-fill it before the call (quadrants beyond m are not written); finish with pb_bn_finalize. */
+int64_t pb_rgcn_gemm_fwd_bn_partial_rows(int64_t m);
+int pb_rgcn_gemm_fwd_bn(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                        const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                        int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype, float* bn_partials,
+                        pb_stream_t stream);
 /* dA [M,K] = g[M,d] @ Wcat^T.  g_* is the GEMM-operand copy of the output gradient (bf16, or f32 hi/lo);
  * dA is bf16 (PB_BF16) or f32 (PB_F32). */
 int pb_rgcn_gemm_bwd_data(const void* g_hi, const void* g_lo, int64_t ldg, const void* wcat_hi,
@@ -264,6 +273,10 @@ int pb_bn_stats(const void* out, int64_t ldo, int64_t m, int32_t d, const pb_gro
                 const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                 float* save_mean_rstd, float* bn_coef, void* workspace, size_t workspace_bytes, int32_t act_dtype,
                 pb_stream_t stream);
+/* mean / var / running statistics / bn_coef from unshifted column partials f32 [n_partials, 2, d] over m_valid rows. */
+int pb_bn_finalize(const float* partials, int64_t n_partials, int64_t m_valid, int32_t d, const float* gamma,
+                   const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                   float* save_mean_rstd, float* bn_coef, pb_stream_t stream);
 int pb_bn_prepare_eval(const float* gamma, const float* beta, const float* running_mean,
                        const float* running_var, float eps, int32_t d, float* bn_coef,
                        pb_stream_t stream);

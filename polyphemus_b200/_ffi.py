@@ -68,6 +68,10 @@ SIGNATURES = {
     "pb_weight_prep": (c_int, [_P, _P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P]),
     "pb_rgcn_gemm_fwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
                                  POINTER(GroupsStruct), c_int32, c_int32, _P]),
+    "pb_rgcn_gemm_fwd_bn_partial_rows": (c_int64, [c_int64]),
+    "pb_rgcn_gemm_fwd_bn": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
+                                    POINTER(GroupsStruct), c_int32, c_int32, _P, _P]),
+    "pb_bn_finalize": (c_int, [_P, c_int64, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P, _P, _P, _P]),
     "pb_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, _P]),
     "pb_rgcn_gemm_bwd_data": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int64, c_int64, c_int32, c_int32,
                                       POINTER(GroupsStruct), c_int32, _P]),
@@ -130,7 +134,7 @@ def lib() -> ctypes.CDLL:
 LAUNCHES = {
     "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
     "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_edge_table_bwd_fused": 2, "pb_agg_bwd_fused": 1, "pb_csr_visit_meta": 1, "pb_csr_bwd_stream": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
-    "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
+    "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_fwd_bn": 1, "pb_bn_finalize": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_ce_rows_fwd": 1, "pb_ce_rows_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,
     "pb_bar_pool_fwd": 1, "pb_bar_pool_bwd": 1, "pb_bar_expand_fwd": 1, "pb_bar_expand_bwd": 1,

@@ -197,7 +197,7 @@ __global__ void bn_stats_finalize_kernel(const float* __restrict__ partials, int
   const int c = blockIdx.x * 32 + threadIdx.x;
   const double s1 = s[0], s2 = s[1];
   const double n = (double)m;
-  const double mean = (double)act_ld1(shift_row, c, abf) + s1 / n;
+  const double mean = (shift_row ? (double)act_ld1(shift_row, c, abf) : 0.0) + s1 / n;   // shift_row NULL: unshifted sums
   double var = (s2 - s1 * s1 / n) / n;
   if (var < 0.0) var = 0.0;
   const float meanf = (float)mean, varf = (float)var;
@@ -408,6 +408,20 @@ extern "C" int pb_bn_stats(const void* out, int64_t ldo, int64_t m, int32_t d, c
   bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, st>>>(partials, ctas, shift_row, abf, mv, d, gamma, beta, eps,
                                                                            momentum, running_mean, running_var,
                                                                            save_mean_rstd, bn_coef);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// Statistics from column partials [n_partials][2][d] (sum, sum of squares; unshifted) that another kernel left behind —
+// the forward GEMM's epilogue (pb_rgcn_gemm_fwd_bn) — instead of a second pass over `out`.
+extern "C" int pb_bn_finalize(const float* partials, int64_t n_partials, int64_t m_valid, int32_t d, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                              float* save_mean_rstd, float* bn_coef, pb_stream_t stream) {
+  PB_REQUIRE(partials && gamma && beta && save_mean_rstd && bn_coef, "pb_bn_finalize: null pointer");
+  PB_REQUIRE(n_partials > 0 && n_partials < ((int64_t)1 << 31) && m_valid > 0 && d > 0, "pb_bn_finalize: bad sizes");
+  bn_stats_finalize_kernel<<<(d + 31) / 32, dim3(32, kFinLanes), 0, as_stream(stream)>>>(
+      partials, (int)n_partials, nullptr, false, m_valid, d, gamma, beta, eps, momentum, running_mean, running_var,
+      save_mean_rstd, bn_coef);
   PB_LAUNCH_CHECK();
   return PB_OK;
 }

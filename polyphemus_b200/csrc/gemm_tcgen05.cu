@@ -49,6 +49,11 @@ struct GemmParams {
   int remap_d;
   int n_groups;
   long long grp_start[4];
+  // BatchNorm statistics as a by-product of the forward epilogue: per (m-tile, lane quadrant) the column sums and sums of
+  // squares of the STORED output values over the quadrant's real rows (padding rows of a group excluded), f32
+  // [num_m_tiles * 4][2][n]. nullptr = off.
+  float* bn_partials;
+  long long grp_count[4];
 };
 
 template <bool BF16>
@@ -221,6 +226,21 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
     // writes whole 64/128-byte row segments instead of 32 scattered 16-byte pieces.
     uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 +
                      (warp < 6 ? (warp - 2) * C::kEpiStageBytes : 4 * C::kEpiStageBytes + (warp - 6) * C::kEpiStageBytesBf16);
+    int bn_valid = 0;           // real rows of this warp's quadrant in the current tile (BatchNorm partials)
+    size_t bn_row = 0;          // partial row (m-tile * 4 + quadrant)
+    auto bn_chunk = [&](int col, bool bf16_rows) {
+      // column `col + lane` of the staged 32 x 32 chunk, summed over the quadrant's real rows in row order
+      float s1 = 0.f, s2 = 0.f;
+      for (int r = 0; r < bn_valid; ++r) {
+        const float x = bf16_rows ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stage + r * C::kStageRowBf16 + 2 * lane))
+                                  : *reinterpret_cast<const float*>(stage + r * C::kStageRowF32 + 4 * lane);
+        s1 += x;
+        s2 += x * x;
+      }
+      float* dst = p.bn_partials + bn_row * 2 * (size_t)p.n + col + lane;
+      dst[0] = s1;
+      dst[p.n] = s2;
+    };
     auto store_chunk = [&](const float* v, int64_t row0, int col, int split) {
       if (p.out_bf16) {
         uint8_t* mine = stage + lane * C::kStageRowBf16;
@@ -243,6 +263,7 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
           const uint4 q = *reinterpret_cast<const uint4*>(stage + r * C::kStageRowBf16 + c16 * 16);
           if (row0 + r < p.m) *reinterpret_cast<uint4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 8) = q;
         }
+        if (p.bn_partials) bn_chunk(col, true);
       } else {
         uint8_t* mine = stage + lane * C::kStageRowF32;
         float4 bq[8];
@@ -260,6 +281,7 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
           const float4 q = *reinterpret_cast<const float4*>(stage + r * C::kStageRowF32 + c16 * 16);
           if (row0 + r < p.m) *reinterpret_cast<float4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 4) = q;
         }
+        if (p.bn_partials) bn_chunk(col, false);
       }
       __syncwarp();   // staging buffer is reused by the next chunk
     };
@@ -271,6 +293,18 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
       const int kb1 = p.split_kb[split + 1];
       const int64_t row0 = m0 + quad * 32;      // first row of this warp's TMEM lane quadrant
       const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+      if (p.bn_partials) {
+        long long lim = p.m;                     // end of the real rows this tile can hold
+        if (p.n_groups > 0) {
+          int grp = 0;
+          for (int g = p.n_groups - 1; g >= 0; --g)
+            if (p.grp_start[g] <= m0) { grp = g; break; }
+          lim = p.grp_start[grp] + p.grp_count[grp];
+        }
+        const long long nv = lim - row0;
+        bn_valid = nv < 0 ? 0 : (nv > 32 ? 32 : (int)nv);
+        bn_row = (size_t)(mn / p.num_n_tiles) * 4 + quad;
+      }
       if constexpr (BF16) {
         // single accumulation: stream TMEM -> registers -> global
         mbar_wait(tmem_full + buf, buf_phase);
@@ -480,7 +514,7 @@ template <bool BF16>
 static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n, int64_t k, void* out, int64_t ldd,
                        bool out_bf16, const float* bias, int num_splits, int64_t split_stride, cudaStream_t st,
                        const pb_groups_t* groups = nullptr, int remap_mode = 0, int remap_d = 0,
-                       const int* split_table = nullptr) {
+                       const int* split_table = nullptr, float* bn_partials = nullptr) {
   using C = Cfg<BF16>;
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -517,8 +551,9 @@ static int launch_gemm(const Operand& a, const Operand& b, int64_t m, int64_t n,
     p.remap_mode = remap_mode;
     p.remap_d = remap_d;
     p.n_groups = groups->n_groups;
-    for (int g = 0; g < groups->n_groups && g < 4; ++g) p.grp_start[g] = groups->start[g];
+    for (int g = 0; g < groups->n_groups && g < 4; ++g) { p.grp_start[g] = groups->start[g]; p.grp_count[g] = groups->count[g]; }
   }
+  p.bn_partials = bn_partials;
   const int64_t total = (int64_t)p.num_m_tiles * p.num_n_tiles * p.num_splits;
   const int grid = (int)std::min<int64_t>(total, sm_count());
   // the dynamic shared-memory limit is a per-device function attribute: set it once on every device that launches
@@ -567,10 +602,10 @@ static int bwd_weight_splits(int64_t m, int d, int k, bool bf16) {
 
 using namespace pb;
 
-extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
-                                const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
-                                int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype,
-                                pb_stream_t stream) {
+static int rgcn_gemm_fwd_impl(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                              const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                              int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype, float* bn_partials,
+                              pb_stream_t stream) {
   int rc = check_gemm_dims(m, d, k, dtype, "pb_rgcn_gemm_fwd");
   if (rc) return rc;
   PB_REQUIRE(act_dtype == PB_F32 || (act_dtype == PB_BF16 && dtype == PB_BF16),
@@ -585,9 +620,28 @@ extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda,
   Operand a{a_hi, a_lo, m, k, lda, false};
   Operand b{wcat_t_hi, wcat_t_lo, d, kw, kw, false};
   cudaStream_t st = as_stream(stream);
-  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, out_bf16, bias, 1, 0, st, groups, 1, d)
-                        : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d);
+  rc = dtype == PB_BF16 ? launch_gemm<true>(a, b, m, d, k, out, ldo, out_bf16, bias, 1, 0, st, groups, 1, d, nullptr, bn_partials)
+                        : launch_gemm<false>(a, b, m, d, k, out, ldo, false, bias, 1, 0, st, groups, 1, d, nullptr, bn_partials);
   return rc < 0 ? rc : PB_OK;
+}
+
+extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                                const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                                int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype,
+                                pb_stream_t stream) {
+  return rgcn_gemm_fwd_impl(a_hi, a_lo, lda, wcat_t_hi, wcat_t_lo, bias, out, ldo, m, d, k, groups, dtype, act_dtype, nullptr,
+                            stream);
+}
+
+extern "C" int64_t pb_rgcn_gemm_fwd_bn_partial_rows(int64_t m) { return m <= 0 ? 0 : (m + 127) / 128 * 4; }
+
+extern "C" int pb_rgcn_gemm_fwd_bn(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
+                                   const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
+                                   int32_t k, const pb_groups_t* groups, int32_t dtype, int32_t act_dtype,
+                                   float* bn_partials, pb_stream_t stream) {
+  PB_REQUIRE(bn_partials, "pb_rgcn_gemm_fwd_bn: null bn_partials");
+  return rgcn_gemm_fwd_impl(a_hi, a_lo, lda, wcat_t_hi, wcat_t_lo, bias, out, ldo, m, d, k, groups, dtype, act_dtype,
+                            bn_partials, stream);
 }
 
 // Generic D[m,n] = A[m,k] . B[n,k]^T (+ bias[n]) on the same kernel: any nn.Linear forward / input gradient.

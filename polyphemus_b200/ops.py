@@ -53,6 +53,8 @@ _bf16_activations = os.environ.get("PB200_BF16_ACT", "1") != "0"
 # "fused" (default): scatter-by-source and the edge-table gradient in one pass, shared-memory accumulators with
 # thread-owned columns; "legacy": the round-1 pair of kernels with the E x d intermediate (kept for A/B measurements)
 _agg_bwd_mode = os.environ.get("PB200_AGG_BWD", "fused")
+# BatchNorm batch statistics as a by-product of the forward GEMM's epilogue (default) or by pb_bn_stats' own pass over `out`
+_bn_stats_in_epilogue = os.environ.get("PB200_BN_EPILOGUE", "1") != "0"
 
 
 def set_bf16_activations(enabled: bool) -> None:
@@ -176,8 +178,15 @@ class RGCLayerFn(torch.autograd.Function):
             ctx.keep_bits = keep_bits
             _, _, wt_hi, wt_lo = _weights(weight, root, n_w, d, cfg.dtype, st)
             out = torch.empty((n, d), dtype=x.dtype, device=dev)
-            _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
-                  _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, act, st)
+            fuse_stats = cfg.batch_norm and cfg.training and _bn_stats_in_epilogue
+            if fuse_stats:       # BatchNorm column sums leave the GEMM epilogue: no second pass over `out`
+                n_part = int(_ffi.lib().pb_rgcn_gemm_fwd_bn_partial_rows(n))
+                bn_part = torch.zeros((n_part, 2, d), dtype=torch.float32, device=dev)
+                _call("pb_rgcn_gemm_fwd_bn", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
+                      _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, act, bn_part.data_ptr(), st)
+            else:
+                _call("pb_rgcn_gemm_fwd", a_hi.data_ptr(), _ffi.ptr(a_lo), k, wt_hi.data_ptr(), _ffi.ptr(wt_lo),
+                      _ffi.ptr(bias_c), out.data_ptr(), d, n, d, k, groups, cfg.dtype, act, st)
             ctx.operand = (a_hi, a_lo) if cfg.save_operand else None
             ctx.struct = struct
             if not cfg.batch_norm:
@@ -186,7 +195,11 @@ class RGCLayerFn(torch.autograd.Function):
                 return out
             coef = torch.empty((3, d), dtype=torch.float32, device=dev)
             save = torch.empty((2, d), dtype=torch.float32, device=dev)
-            if cfg.training:
+            if fuse_stats:
+                n_valid = n if struct is None else sum(struct.counts)
+                _call("pb_bn_finalize", bn_part.data_ptr(), n_part, n_valid, d, gamma.data_ptr(), beta.data_ptr(), cfg.eps,
+                      cfg.momentum, _ffi.ptr(running_mean), _ffi.ptr(running_var), save.data_ptr(), coef.data_ptr(), st)
+            elif cfg.training:
                 ws_bytes = _ffi.lib().pb_bn_workspace_bytes(n, d)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
                 _call("pb_bn_stats", out.data_ptr(), d, n, d, groups, gamma.data_ptr(), beta.data_ptr(), cfg.eps,

@@ -723,3 +723,63 @@ def test_token_hist_matches_bincount(cuda):
             sel = ids[is_drum.cpu() == bool(s_)]
             want = torch.cat((torch.bincount(sel[..., 0].reshape(-1), minlength=131), torch.bincount(sel[..., 1].reshape(-1), minlength=99)))
             assert torch.equal(counts[s_].cpu(), want)
+
+
+@pytest.mark.parametrize("dtype_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("structured", [True, False])
+def test_gemm_fwd_bn_partials_and_finalize(cuda, dtype_name, structured):
+    """BatchNorm statistics as a by-product of the forward GEMM's epilogue (pb_rgcn_gemm_fwd_bn + pb_bn_finalize) ==
+    the separate pass (pb_bn_stats) over the stored output: mean / rstd / running statistics, padding rows excluded."""
+    import ctypes
+    from test_parity_scale_gpu import _groups
+    ffi = _ffi()
+    dtype = ffi.PB_BF16 if dtype_name == "bf16" else ffi.PB_F32
+    act = dtype                                             # bf16 mode stores `out` in bf16
+    d = 512
+    gen = torch.Generator().manual_seed(11)
+    if structured:
+        counts = (300, 0, 129, 1000)
+        gs, starts, m = _groups(ffi, counts)
+        gref, k = ctypes.byref(gs), 4 * d
+        valid = torch.zeros(m, dtype=torch.bool)
+        for g in range(4):
+            valid[starts[g]:starts[g] + counts[g]] = True
+        kw = 7 * d
+    else:
+        m, k, gref, kw = 1000, 7 * d, None, 7 * d
+        valid = torch.ones(m, dtype=torch.bool)
+    a = torch.randn(m, k, generator=gen) * valid.unsqueeze(1)
+    wt = torch.randn(d, kw, generator=gen) / np.sqrt(k)
+    bias = torch.randn(d, generator=gen)
+    a_hi, a_lo = operands(a.to(cuda), dtype)
+    w_hi, w_lo = operands(wt.to(cuda), dtype)
+    bias_dev = bias.to(cuda)
+    odt = torch.bfloat16 if dtype == ffi.PB_BF16 else torch.float32
+    out = torch.empty((m, d), dtype=odt, device=cuda)
+    lib = ffi.lib()
+    n_part = lib.pb_rgcn_gemm_fwd_bn_partial_rows(m)
+    parts = torch.zeros((n_part, 2, d), device=cuda)
+    ffi.check(lib.pb_rgcn_gemm_fwd_bn(ptr(a_hi), ptr(a_lo), k, ptr(w_hi), ptr(w_lo), ptr(bias_dev), ptr(out), d, m, d, k, gref,
+                                      dtype, act, ptr(parts), st()), "gemm_fwd_bn")
+    stored = out.float().double().cpu()[valid]
+    torch.testing.assert_close(parts[:, 0].sum(0).double().cpu(), stored.sum(0), rtol=1e-5, atol=1e-3)
+    torch.testing.assert_close(parts[:, 1].sum(0).double().cpu(), (stored ** 2).sum(0), rtol=1e-5, atol=1e-3)
+    gamma, beta = (torch.rand(d, generator=gen) + 0.5).to(cuda), torch.randn(d, generator=gen).to(cuda)
+    res = []
+    for fused in (True, False):
+        rm, rv = torch.zeros(d, device=cuda), torch.ones(d, device=cuda)
+        save, coef = torch.empty(2, d, device=cuda), torch.empty(3, d, device=cuda)
+        if fused:
+            ffi.check(lib.pb_bn_finalize(ptr(parts), n_part, int(valid.sum()), d, ptr(gamma), ptr(beta), 1e-5, 0.1, ptr(rm), ptr(rv),
+                                         ptr(save), ptr(coef), st()), "bn_finalize")
+        else:
+            ws_bytes = lib.pb_bn_workspace_bytes(m, d)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cuda)
+            ffi.check(lib.pb_bn_stats(ptr(out), d, m, d, gref, ptr(gamma), ptr(beta), 1e-5, 0.1, ptr(rm), ptr(rv), ptr(save), ptr(coef),
+                                      ptr(ws), ws_bytes, act, st()), "bn_stats")
+        res.append((rm, rv, save, coef))
+    for x, y in zip(*res):
+        torch.testing.assert_close(x, y, rtol=2e-5, atol=2e-6)
+    want_mean, want_var = stored.mean(0), stored.var(0, unbiased=False)
+    torch.testing.assert_close(res[0][2][0].double().cpu(), want_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res[0][2][1].double().cpu(), 1 / torch.sqrt(want_var + 1e-5), rtol=1e-5, atol=1e-6)
