@@ -366,6 +366,16 @@ int pb_bar_expand_bwd(const float* g_x, int64_t ldg, const int32_t* bar_ptr, int
                       pb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Row permutation into / out of the structured layout, fused with the activation-storage conversion (f32 <-> bf16):
+ *   scatter: dst[pos[v]] = src[v] for v < n, the padding rows of every group of dst [n_rows, d] written as zero;
+ *   gather : dst[v] = src[pos[v]].   pos i64 [n] is injective (node -> padded row). Each is the other's gradient.
+ * ---------------------------------------------------------------------------------------------- */
+int pb_rows_scatter(const void* src, int32_t src_dtype, const int64_t* pos, int64_t n, int32_t d, void* dst,
+                    int32_t dst_dtype, int64_t n_rows, const pb_groups_t* groups, pb_stream_t stream);
+int pb_rows_gather(const void* src, int32_t src_dtype, const int64_t* pos, int64_t n, int32_t d, void* dst,
+                   int32_t dst_dtype, pb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Data formats either side of the path.
  *   pb_dataset_structure / pb_dataset_tokens — replace PolyphemusDataset.__getitem__ (data.py:218-271) for a batch of
  *     samples in the on-disk layout of preprocess.py:210: s_disk u8/bool [B, 4, T], c_disk int16 [B, 4, T, 16, 2],

@@ -101,6 +101,8 @@ SIGNATURES = {
     "pb_ce_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
     "pb_ce_rows_fwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P]),
     "pb_ce_rows_bwd": (c_int, [_P, c_int64, c_int32, c_int64, c_int32, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+    "pb_rows_scatter": (c_int, [_P, c_int32, _P, c_int64, c_int32, _P, c_int32, c_int64, POINTER(GroupsStruct), _P]),
+    "pb_rows_gather": (c_int, [_P, c_int32, _P, c_int64, c_int32, _P, c_int32, _P]),
     "pb_token_hist": (c_int, [_P, c_int64, c_int32, c_int32, _P, c_int64, c_int32, c_int32, _P, _P]),
     "pb_dataset_structure": (c_int, [_P, c_int64, c_int32, _P, _P]),
     "pb_dataset_tokens": (c_int, [_P, _P, _P, c_int64, c_int32, _P, _P]),
@@ -133,7 +135,7 @@ def lib() -> ctypes.CDLL:
 # host-only queries are not counted).
 LAUNCHES = {
     "pb_graph_count": 8, "pb_graph_fill": 1, "pb_edge_attrs_encode": 1, "pb_edge_attrs_decode": 1, "pb_csr_build": 13,
-    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_edge_table_bwd_fused": 2, "pb_agg_bwd_fused": 1, "pb_csr_visit_meta": 1, "pb_csr_bwd_stream": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
+    "pb_edge_table_fwd": 1, "pb_edge_table_bwd": 2, "pb_edge_table_bwd_fused": 2, "pb_agg_bwd_fused": 1, "pb_csr_visit_meta": 1, "pb_rows_scatter": 2, "pb_rows_gather": 1, "pb_csr_bwd_stream": 1, "pb_agg_fwd": 1, "pb_agg_bwd": 2, "pb_dropout_mask": 1, "pb_dropout_bits": 1,
     "pb_weight_prep": 1, "pb_rgcn_gemm_fwd": 1, "pb_rgcn_gemm_fwd_bn": 1, "pb_bn_finalize": 1, "pb_rgcn_gemm_bwd_data": 1, "pb_gemm_nt": 1, "pb_rgcn_gemm_bwd_weight": 2,
     "pb_gemm_f32_check": 1, "pb_bn_stats": 2, "pb_bn_prepare_eval": 1, "pb_bn_relu_res_fwd": 1,
     "pb_bn_relu_res_bwd": 4, "pb_grad_prep": 2, "pb_ce_fwd": 1, "pb_ce_bwd": 1, "pb_ce_rows_fwd": 1, "pb_ce_rows_bwd": 1, "pb_chord_embed_fwd": 1, "pb_chord_embed_bwd_prep": 1,

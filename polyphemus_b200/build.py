@@ -20,7 +20,7 @@ OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB_PATH = os.path.join(LIB_DIR, "libpolyphemus_b200.so")
 HEADER = os.path.join(os.path.dirname(PKG_DIR), "include", "polyphemus_b200.h")
 
-SOURCES = ["common.cu", "graph_build.cu", "csr.cu", "aggregate.cu", "agg_bwd_tc.cu", "bn.cu", "loss.cu", "chord.cu", "pool.cu", "dataset.cu", "gemm_check.cu", "gemm_tcgen05.cu"]
+SOURCES = ["common.cu", "graph_build.cu", "csr.cu", "aggregate.cu", "agg_bwd_tc.cu", "bn.cu", "loss.cu", "chord.cu", "pool.cu", "dataset.cu", "rows.cu", "gemm_check.cu", "gemm_tcgen05.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--extended-lambda",
     "-Xcompiler", "-fPIC",

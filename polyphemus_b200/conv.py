@@ -163,11 +163,10 @@ class GCN(nn.Module):
             # bf16 mode: the stack keeps its activations (x, the pre-BatchNorm output, y and their gradients) in bf16
             # between the kernels — 16-bit storage as under the reference's fp16 autocast, fp32 arithmetic inside
             act_bf16 = (self.layers[0].precision or ops.get_precision()) == "bf16" and ops.bf16_activations_enabled()
-            xp = ops.ScatterRowsFn.apply(x.to(torch.bfloat16) if act_bf16 else x, st.pos, st.n_padded)
+            xp = ops.ScatterRowsFn.apply(x, st, torch.bfloat16 if act_bf16 else torch.float32)
             for i, layer in enumerate(self.layers):
                 xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st)
-            out = ops.GatherRowsFn.apply(xp, st.pos)
-            return out.float() if act_bf16 else out
+            return ops.GatherRowsFn.apply(xp, st, torch.float32)
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):
             residual = x

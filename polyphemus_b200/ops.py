@@ -437,35 +437,58 @@ def tc_linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return TensorCoreLinearFn.apply(x, weight, bias, dtype, out_bf16)
 
 
+def _act_code(dtype: torch.dtype) -> int:
+    return _ffi.PB_BF16 if dtype == torch.bfloat16 else _ffi.PB_F32
+
+
+def _rows_scatter(x, pos, struct, out_dtype):
+    out = torch.empty((struct.n_padded, x.size(1)), dtype=out_dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        _call("pb_rows_scatter", x.data_ptr(), _act_code(x.dtype), pos.data_ptr(), x.size(0), x.size(1), out.data_ptr(),
+              _act_code(out_dtype), struct.n_padded, struct.groups_ref(), _ffi.stream())
+    return out
+
+
+def _rows_gather(xp, pos, out_dtype):
+    out = torch.empty((pos.numel(), xp.size(1)), dtype=out_dtype, device=xp.device)
+    with torch.cuda.device(xp.device):
+        _call("pb_rows_gather", xp.data_ptr(), _act_code(xp.dtype), pos.data_ptr(), pos.numel(), xp.size(1), out.data_ptr(),
+              _act_code(out_dtype), _ffi.stream())
+    return out
+
+
 class ScatterRowsFn(torch.autograd.Function):
-    """out = zeros(n_rows, d); out[pos] = x for an injective row map ``pos`` (node -> padded row of the structured
-    layout). The gradient is a plain gather — autograd's own formula for index_copy / index_select goes through
-    index_add_ (atomic adds), which an injective map does not need."""
+    """Entry of a structured GCN stack: out = zeros(n_padded, d) in ``out_dtype``; out[pos] = x (node -> padded row of
+    the structured layout, injective). One kernel incl. the fp32 -> bf16 storage conversion and the zeroed padding rows
+    (pb_rows_scatter); the gradient is the matching gather (autograd's own formula for index_copy goes through
+    index_add_ with atomic adds, which an injective map does not need)."""
 
     @staticmethod
-    def forward(ctx, x, pos, n_rows: int):
-        ctx.save_for_backward(pos)
-        return torch.zeros((n_rows, x.size(1)), dtype=x.dtype, device=x.device).index_copy_(0, pos, x)
+    def forward(ctx, x, struct, out_dtype):
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.float()
+        ctx.struct, ctx.x_dtype = struct, x.dtype
+        return _rows_scatter(x.contiguous(), struct.pos, struct, out_dtype)
 
     @staticmethod
     def backward(ctx, g):
-        (pos,) = ctx.saved_tensors
-        return g.index_select(0, pos), None, None
+        return _rows_gather(g.contiguous(), ctx.struct.pos, ctx.x_dtype), None, None
 
 
 class GatherRowsFn(torch.autograd.Function):
-    """out = xp[pos] for an injective ``pos``; the gradient scatters with index_copy_ (rows nobody read get zero)."""
+    """Exit of a structured GCN stack: out = xp[pos] in ``out_dtype`` (pb_rows_gather); the gradient scatters back
+    (rows nobody read — the padding — get zero)."""
 
     @staticmethod
-    def forward(ctx, xp, pos):
-        ctx.save_for_backward(pos)
-        ctx.n_rows = xp.size(0)
-        return xp.index_select(0, pos)
+    def forward(ctx, xp, struct, out_dtype):
+        ctx.struct, ctx.xp_dtype = struct, xp.dtype
+        return _rows_gather(xp.contiguous(), struct.pos, out_dtype)
 
     @staticmethod
     def backward(ctx, g):
-        (pos,) = ctx.saved_tensors
-        return torch.zeros((ctx.n_rows, g.size(1)), dtype=g.dtype, device=g.device).index_copy_(0, pos, g), None
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        return _rows_scatter(g.contiguous(), ctx.struct.pos, ctx.struct, ctx.xp_dtype), None, None
 
 
 class BarPoolFn(torch.autograd.Function):
