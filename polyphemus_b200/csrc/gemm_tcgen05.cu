@@ -226,10 +226,29 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
     // writes whole 64/128-byte row segments instead of 32 scattered 16-byte pieces.
     uint8_t* stage = smem + C::kStages * C::kStageBytes + 256 +
                      (warp < 6 ? (warp - 2) * C::kEpiStageBytes : 4 * C::kEpiStageBytes + (warp - 6) * C::kEpiStageBytesBf16);
-    int bn_valid = 0;           // real rows of this warp's quadrant in the current tile (BatchNorm partials)
-    size_t bn_row = 0;          // partial row (m-tile * 4 + quadrant)
-    auto bn_chunk = [&](int col, bool bf16_rows) {
-      // column `col + lane` of the staged 32 x 32 chunk, summed over the quadrant's real rows in row order
+    // BatchNorm partials: column sums of the stored values over the real rows of this warp's quadrant, accumulated in
+    // registers across the tiles this (persistent) CTA processes and flushed when the column block changes / at the end
+    constexpr int kBnChunks = C::BN / 32;
+    int bn_valid = 0;           // real rows of this warp's quadrant in the current tile
+    int bn_n0 = -1;             // column block the accumulators belong to
+    float bn_s1[kBnChunks], bn_s2[kBnChunks];
+#pragma unroll
+    for (int i = 0; i < kBnChunks; ++i) { bn_s1[i] = 0.f; bn_s2[i] = 0.f; }
+    auto bn_flush = [&]() {
+      if (bn_n0 < 0) return;
+      float* dst = p.bn_partials + ((size_t)blockIdx.x * 4 + quad) * 2 * (size_t)p.n + bn_n0 + lane;
+#pragma unroll
+      for (int i = 0; i < kBnChunks; ++i) {
+        if (bn_s1[i] != 0.f || bn_s2[i] != 0.f) {      // chunks outside this warp's column half stay untouched
+          dst[32 * i] += bn_s1[i];                     // same thread, same address: plain read-modify-write
+          dst[p.n + 32 * i] += bn_s2[i];
+        }
+        bn_s1[i] = 0.f;
+        bn_s2[i] = 0.f;
+      }
+    };
+    auto bn_chunk = [&](int ci, bool bf16_rows) {
+      // column (chunk ci, lane) of the staged 32 x 32 chunk, summed over the quadrant's real rows in row order
       float s1 = 0.f, s2 = 0.f;
       for (int r = 0; r < bn_valid; ++r) {
         const float x = bf16_rows ? __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stage + r * C::kStageRowBf16 + 2 * lane))
@@ -237,11 +256,11 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
         s1 += x;
         s2 += x * x;
       }
-      float* dst = p.bn_partials + bn_row * 2 * (size_t)p.n + col + lane;
-      dst[0] = s1;
-      dst[p.n] = s2;
+#pragma unroll
+      for (int i = 0; i < kBnChunks; ++i)
+        if (i == ci) { bn_s1[i] += s1; bn_s2[i] += s2; }
     };
-    auto store_chunk = [&](const float* v, int64_t row0, int col, int split) {
+    auto store_chunk = [&](const float* v, int64_t row0, int col, int split, int ci) {
       if (p.out_bf16) {
         uint8_t* mine = stage + lane * C::kStageRowBf16;
 #pragma unroll
@@ -263,7 +282,7 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
           const uint4 q = *reinterpret_cast<const uint4*>(stage + r * C::kStageRowBf16 + c16 * 16);
           if (row0 + r < p.m) *reinterpret_cast<uint4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 8) = q;
         }
-        if (p.bn_partials) bn_chunk(col, true);
+        if (p.bn_partials) bn_chunk(ci, true);
       } else {
         uint8_t* mine = stage + lane * C::kStageRowF32;
         float4 bq[8];
@@ -281,7 +300,7 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
           const float4 q = *reinterpret_cast<const float4*>(stage + r * C::kStageRowF32 + c16 * 16);
           if (row0 + r < p.m) *reinterpret_cast<float4*>(o + (size_t)(row0 + r) * p.ldd + c16 * 4) = q;
         }
-        if (p.bn_partials) bn_chunk(col, false);
+        if (p.bn_partials) bn_chunk(ci, false);
       }
       __syncwarp();   // staging buffer is reused by the next chunk
     };
@@ -303,18 +322,20 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
         }
         const long long nv = lim - row0;
         bn_valid = nv < 0 ? 0 : (nv > 32 ? 32 : (int)nv);
-        bn_row = (size_t)(mn / p.num_n_tiles) * 4 + quad;
+        if (n0 != bn_n0) { bn_flush(); bn_n0 = n0; }
       }
       if constexpr (BF16) {
         // single accumulation: stream TMEM -> registers -> global
         mbar_wait(tmem_full + buf, buf_phase);
         tc_fence_after();
-#pragma unroll 1
-        for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
+#pragma unroll
+        for (int ci = 0; ci < kBnChunks; ++ci) {
+          const int c0 = 32 * ci;
+          if (c0 < col_lo || c0 >= col_hi) continue;            // warp-uniform: the other warp group's half
           uint32_t v[32];
           tmem_ld_32x32(lane_base + (uint32_t)(buf * C::BN + c0), v);
           if (row0 < p.m && n0 + c0 < p.n)   // warp-uniform; n is a multiple of 32 (host check): whole chunk in range
-            store_chunk(reinterpret_cast<const float*>(v), row0, n0 + c0, split);
+            store_chunk(reinterpret_cast<const float*>(v), row0, n0 + c0, split, ci);
         }
         tc_fence_before();
         __syncwarp();
@@ -345,9 +366,10 @@ __global__ void __launch_bounds__(kGemmThreads<BF16>, 1) gemm_tcgen05_kernel(con
         }
 #pragma unroll
         for (int c0 = 0; c0 < C::BN; c0 += 32)
-          if (row0 < p.m && n0 + c0 < p.n) store_chunk(acc + c0, row0, n0 + c0, split);
+          if (row0 < p.m && n0 + c0 < p.n) store_chunk(acc + c0, row0, n0 + c0, split, c0 / 32);
       }
     }
+    if (p.bn_partials) bn_flush();
   }
 
   tc_fence_before();
@@ -633,7 +655,8 @@ extern "C" int pb_rgcn_gemm_fwd(const void* a_hi, const void* a_lo, int64_t lda,
                             stream);
 }
 
-extern "C" int64_t pb_rgcn_gemm_fwd_bn_partial_rows(int64_t m) { return m <= 0 ? 0 : (m + 127) / 128 * 4; }
+// one partial row per (persistent CTA, lane quadrant): the epilogue accumulates across the tiles a CTA processes
+extern "C" int64_t pb_rgcn_gemm_fwd_bn_partial_rows(int64_t m) { return m <= 0 ? 0 : (int64_t)sm_count() * 4; }
 
 extern "C" int pb_rgcn_gemm_fwd_bn(const void* a_hi, const void* a_lo, int64_t lda, const void* wcat_t_hi,
                                    const void* wcat_t_lo, const float* bias, void* out, int64_t ldo, int64_t m, int32_t d,
