@@ -176,7 +176,11 @@ class RGCLayerFn(torch.autograd.Function):
             _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
                   cfg.dtype, _ffi.ptr(keep_bits), p, act, st)
             ctx.keep_bits = keep_bits
-            _, _, wt_hi, wt_lo = _weights(weight, root, n_w, d, cfg.dtype, st)
+            # one operand preparation per layer call: the transposed copy feeds this GEMM, the other one the input
+            # gradient in backward (kept in ctx: 3.7 MB at d = 512 in bf16)
+            w_hi, w_lo, wt_hi, wt_lo = _weights(weight, root, n_w, d, cfg.dtype, st)
+            ctx.w_operand = (w_hi, w_lo)
+            ctx.table = table
             out = torch.empty((n, d), dtype=x.dtype, device=dev)
             fuse_stats = cfg.batch_norm and cfg.training and _bn_stats_in_epilogue
             if fuse_stats:       # BatchNorm column sums leave the GEMM epilogue: no second pass over `out`
@@ -252,7 +256,7 @@ class RGCLayerFn(torch.autograd.Function):
             else:
                 _call("pb_grad_prep", gy.data_ptr(), d, n, d, cfg.dtype, g_hi.data_ptr(), _ffi.ptr(g_lo), d,
                       g_bias.data_ptr(), ws.data_ptr(), ws_bytes, st)
-            table = _edge_table(nn_w, nn_b, d, st)
+            table = ctx.table
             p = cfg.p_drop if cfg.training else 0.0
             if ctx.operand is not None:
                 a_hi, a_lo = ctx.operand
@@ -261,7 +265,11 @@ class RGCLayerFn(torch.autograd.Function):
                 a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
                 _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
                       cfg.dtype, _ffi.ptr(ctx.keep_bits), p, act, st)
-            w_hi, w_lo, _, _ = _weights(weight, root, n_w, d, cfg.dtype, st)
+            if ctx.w_operand is not None:
+                w_hi, w_lo = ctx.w_operand
+                ctx.w_operand = None
+            else:
+                w_hi, w_lo, _, _ = _weights(weight, root, n_w, d, cfg.dtype, st)
             kw = (n_w + 1) * d
             # structured layout: one split-K launch whose splits follow the row groups + a grouped reduce that sums
             # the track block per group (weight[0..3]) and the onset / next / root blocks over all rows

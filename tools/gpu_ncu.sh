@@ -1,16 +1,17 @@
 #!/bin/bash
 # ncu evidence for profiles/: launch list of ONE timed step + one --set full capture per dominant kernel.
 # Numbers printed by bench.py under ncu are never bench values.
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
-B="python bench.py --steps 1 --warmup 3 --skip-e2e --no-cpu-baseline --profiler-range"
+B="python bench.py --steps 1 --warmup 3 --skip-e2e --no-cpu-baseline --no-secondary --profiler-range"
 run() { name=$1; shift; timeout 900 "$@" > gpurun_out/$name.log 2>&1; echo "$name exit=$?"; }
 run t_launch ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_$TAG.csv $B
-for spec in ${SPECS:-aggfwd:agg_fwd_kernel aggbwd:agg_bwd_dx_kernel distred:dist_reduce_kernel gemm:gemm_tcgen05_kernel bn:bn_ dropbits:dropout_bits ce:ce_rows_kernel chord:chord_embed pool:bar_}; do
+for spec in ${SPECS:-aggfwd:agg_fwd_kernel aggbwdtc:agg_bwd_tc_kernel gemm:gemm_tcgen05_kernel bn:bn_ dropbits:dropout_bits ce:ce_rows_kernel chord:chord_embed pool:bar_ rows:rows_permute}; do
   name=${spec%%:*}; rx=${spec##*:}; cnt=1; skip=8
-  case $name in ce|chord|pool) skip=0;; esac
+  case $name in ce|chord|pool|rows) skip=0;; esac
+  [ $name = rows ] && cnt=2
   [ $name = gemm ] && cnt=3
-  [ $name = bn ] && cnt=4
+  [ $name = bn ] && cnt=5
   [ $name = ce ] && cnt=2
   [ $name = chord ] && cnt=2
   [ $name = pool ] && cnt=4

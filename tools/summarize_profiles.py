@@ -82,11 +82,18 @@ def traffic_json():
     families = {   # ABI call -> (summary file, kernel-name prefixes whose launches make up one call)
         "pb_agg_fwd": ("aggfwd", ["agg_fwd_kernel"]),
         "pb_agg_bwd": ("aggbwd", ["agg_bwd_dx_kernel"]),
+        "pb_agg_bwd_fused": ("aggbwdtc", ["agg_bwd_tc_kernel"]),
         "pb_dist_reduce": ("distred", ["dist_reduce_kernel"]),
         "pb_rgcn_gemm_fwd": ("gemm", ["gemm_tcgen05_kernel"]),
-        "pb::gemm_tcgen05_kernel": ("gemm", ["gemm_tcgen05_kernel"]),     # mean of the captured launches
+        "pb::gemm_tcgen05_kernel": ("gemm", ["gemm_tcgen05_kernel"]),     # mean of the captured launches (fwd, bwd_weight, bwd_data)
         "pb_bn_relu_res_fwd": ("bn", ["bn_apply_kernel"]),
         "pb_bn_stats": ("bn", ["bn_stats_partial_kernel", "bn_stats_finalize_kernel"]),
+        "pb_bn_relu_res_bwd": ("bn", ["bn_bwd_partial_kernel", "bn_bwd_apply_kernel"]),
+        "pb_dropout_bits": ("dropbits", ["dropout_bits_kernel"]),
+        "pb_ce_rows": ("ce", ["ce_rows_kernel"]),
+        "pb_chord_embed_fwd": ("chord", ["chord_embed_fwd_kernel"]),
+        "pb_bar_pool": ("pool", ["bar_pool_fwd_kernel", "bar_pool_bwd_kernel"]),
+        "pb_rows_scatter": ("rows", ["rows_permute_kernel"]),
     }
     out = {}
     for call, (stem, prefixes) in families.items():
@@ -97,7 +104,7 @@ def traffic_json():
         for line in open(path):
             if line.startswith("kernel:"):
                 cur = line.split("kernel:")[1].strip()
-                cur = re.sub(r"^void ", "", cur).split("<")[0].split("(")[0]
+                cur = re.sub(r"^void ", "", cur).split("<")[0].split("(")[0].split("::")[-1]
                 per_kernel.setdefault(cur, []).append(0.0)
             elif cur and ("dram__bytes_read.sum" in line or "dram__bytes_write.sum" in line):
                 val, unit = line.split()[-2:]
@@ -116,7 +123,11 @@ def traffic_json():
         out["pb_agg_bwd"]["kernels"] += out["pb_dist_reduce"]["kernels"]
         out["pb_agg_bwd"]["source"] += f" + profiles/{tag}_ncu_distred.txt"
     out.pop("pb_dist_reduce", None)
-    json.dump(out, open(os.path.join(dst, "traffic.json"), "w"), indent=1)
+    path = os.path.join(dst, "traffic.json")
+    merged = json.load(open(path)) if os.path.exists(path) else {}      # entries of earlier rounds stay unless re-measured
+    merged.update(out)
+    out = merged
+    json.dump(out, open(path, "w"), indent=1)
     print("wrote traffic.json:", {k: round(v["bytes_per_launch"] / 1e6, 1) for k, v in out.items()}, "MB")
 
 
