@@ -17,4 +17,8 @@ for spec in ${SPECS:-aggfwd:agg_fwd_kernel aggbwdtc:agg_bwd_tc_kernel gemm:gemm_
   [ $name = pool ] && cnt=4
   run t_ncu_$name ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:$rx -s $skip -c $cnt -f -o gpurun_out/prof_${name}_$TAG $B
 done
+# summaries are made here (the reports themselves exceed what gpurun copies back); keep the backward's report for source-level work
+python tools/summarize_profiles.py $TAG gpurun_out/summaries_$TAG > gpurun_out/summarize.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+find gpurun_out -name '*.ncu-rep' ! -name 'prof_aggbwdtc_*' -delete
+du -sh gpurun_out

@@ -12,6 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 src, dst = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+if len(sys.argv) > 2:            # on the GPU box: summaries next to the captures (only gpurun_out/ travels back)
+    dst = os.path.join(ROOT, sys.argv[2])
+    os.makedirs(dst, exist_ok=True)
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
