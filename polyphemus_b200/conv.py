@@ -99,7 +99,7 @@ class GCL(nn.Module):
         return self._plan
 
     def forward(self, x, edge_index=None, edge_type=None, edge_attr=None, *, plan: Optional[CsrPlan] = None,
-                bn: Optional[nn.BatchNorm1d] = None, struct=None):
+                bn: Optional[nn.BatchNorm1d] = None, struct=None, drawn=None):
         """``bn`` fuses BatchNorm + ReLU + residual of the enclosing GCN layer (model.py:202-206)."""
         if isinstance(x, tuple) or x is None or x.dtype == torch.long:
             raise NotImplementedError("bipartite / index-valued node inputs are not part of the Polyphemus path")
@@ -119,7 +119,8 @@ class GCL(nn.Module):
             training = self.training
         return ops.rgc_layer(x, self.weight, self.root, self.bias, nn_w, nn_b, plan, batch_norm=bn is not None,
                              training=training, p_drop=self.dropout if self.training else 0.0,
-                             precision=self.precision, struct=struct, **kw)
+                             precision=self.precision, struct=struct, **kw,
+                             **({} if drawn is None else dict(seed=drawn[0], keep_bits=drawn[1])))
 
     def extra_repr(self) -> str:
         return f"{self.in_channels}, {self.out_channels}, num_relations={self.num_relations}, dropout={self.dropout}"
@@ -163,9 +164,14 @@ class GCN(nn.Module):
             # bf16 mode: the stack keeps its activations (x, the pre-BatchNorm output, y and their gradients) in bf16
             # between the kernels — 16-bit storage as under the reference's fp16 autocast, fp32 arithmetic inside
             act_bf16 = (self.layers[0].precision or ops.get_precision()) == "bf16" and ops.bf16_activations_enabled()
+            # GCL.message's dropout masks of all layers (model.py:133) are drawn ahead on a side stream
+            p_msg = self.layers[0].dropout if self.training else 0.0
+            same_p = all(layer.dropout == p_msg or not self.training for layer in self.layers)
+            drawn = ops.prefetch_keep_bits(st.plan, x.size(1), p_msg, len(self.layers)) if same_p else None
             xp = ops.ScatterRowsFn.apply(x, st, torch.bfloat16 if act_bf16 else torch.float32)
             for i, layer in enumerate(self.layers):
-                xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st)
+                xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st,
+                           drawn=None if drawn is None else drawn[i])
             return ops.GatherRowsFn.apply(xp, st, torch.float32)
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):

@@ -375,6 +375,379 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
   }
 }
 
+// ====================================================================================================================
+// Ring variant (bf16 activations): the gradient rows reach the SM without passing through registers.
+//
+// In the kernel above a gather warp has at most three 1 KB rows in flight (its registers), ~40 KB per SM: the warps
+// sit on the long scoreboard (3.1 stalled warps per issue, ncu) while HBM idles at 34 %. Here every gather warp copies
+// the gradient rows dH[dst, slot] of the source it will process NEXT with cp.async (16 bytes per lane, no registers,
+// no L1) straight into the Q stage slots those edges own — already in the swizzled MN-major position of their
+// channels — together with their keep bits, and then processes the current source: it reads its 16 channels of an
+// edge from shared memory and writes q = ds * x back IN PLACE (same address per lane). The four Q stages (128 edges,
+// 128 KB) are landing buffer and UMMA operand at once. The records of a source (row, distance, 1 / |segment|, edge id)
+// come from the plan's record stream (pb_csr_bwd_stream) two sources ahead, its three per-source rows (features,
+// root block, residual) are loaded into registers one source ahead.
+//
+// Flow control needs no extra barriers: a warp waits for its own copies (cp.async groups), and before copying into
+// a stage it checks that the stage's previous MMAs are done (`empty`). That check is a non-blocking test when the warp
+// still has a source to process (then the copies are simply issued after it) and a blocking wait otherwise — a
+// blocked warp only ever waits for positions older than everything it still has to consume, so the oldest unconsumed
+// edge can always proceed. Sources with more than 32 out-edges are processed in chunks of 32 (copy, wait, consume).
+#ifndef PB_RG_WARPS
+#define PB_RG_WARPS 15
+#endif
+constexpr int kRgWarps = PB_RG_WARPS;                  // gather warps
+constexpr int kRgThreads = (kRgWarps + 1) * 32;        // + the MMA warp
+constexpr int kRgSlots = kTcStages * kTcStageEdges;    // edges resident in the Q stages
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.b32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
+template <bool DROPOUT, int CPL>
+__global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
+    const int4* __restrict__ visit_meta, const int* __restrict__ visit_edge_ptr, const int4* __restrict__ stream,
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ table, const __nv_bfloat16* __restrict__ d_a,
+    const __nv_bfloat16* __restrict__ gy_res, __nv_bfloat16* __restrict__ gx, float* __restrict__ partials, int64_t n_nodes,
+    int n_rel, const uint16_t* __restrict__ keep_bits, float keep_scale, uint32_t idesc) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int d = 128 * CPL;
+  constexpr int G16 = (CPL + 3) / 4;
+  constexpr int kMB = d / 128;
+  constexpr int kChunkBytes = kTcStageEdges * 128;
+  constexpr int kQStage = (d / 64) * kChunkBytes;
+  constexpr int kBitsSlot = G16 * 64;                   // keep bits of an edge (bytes)
+  constexpr uint32_t kRow = d * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* q_st = smem;                                            // [kTcStages][kQStage]
+  uint8_t* b_st = q_st + kTcStages * kQStage;                      // [kTcStages][kTcBStage]
+  float* t_s = reinterpret_cast<float*>(b_st + kTcStages * kTcBStage);   // [32][d]
+  uint32_t* t_sign = reinterpret_cast<uint32_t*>(t_s + PB_N_DISTS * d);  // [32][32], as above
+  uint2* mask_lut = reinterpret_cast<uint2*>(t_sign + PB_N_DISTS * 32);   // [16]
+  uint8_t* bits_ring = reinterpret_cast<uint8_t*>(mask_lut + 16);         // [kRgSlots][kBitsSlot]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bits_ring + kRgSlots * kBitsSlot);
+  uint64_t* full = bars;                       // [kTcStages]: q written, one arrival per edge slot
+  uint64_t* empty = bars + kTcStages;          // [kTcStages]: tcgen05.commit -> the stage may be refilled
+  uint64_t* done = bars + 2 * kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = r0 + per < n_nodes ? r0 + per : n_nodes;
+  int e0 = 0, n_edges = 0;
+  if (r0 < r1) {
+    e0 = __ldg(visit_edge_ptr + r0);
+    n_edges = __ldg(visit_edge_ptr + r1) - e0;
+  }
+  const int n_total = (n_edges + kTcStageEdges - 1) / kTcStageEdges;
+
+  if (warp == kRgWarps && lane == 0) {
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, kTcStageEdges); mbar_init(empty + s, 1); }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kRgWarps) tmem_alloc(tmem_slot, kMB * kTcN < 32 ? 32 : kMB * kTcN);
+  for (int i = threadIdx.x; i < PB_N_DISTS * d / 4; i += kRgThreads)
+    reinterpret_cast<float4*>(t_s)[i] = __ldg(reinterpret_cast<const float4*>(table) + i);
+  for (int i = threadIdx.x; i < kTcStages * (kQStage + kTcBStage) / 16; i += kRgThreads)
+    reinterpret_cast<uint4*>(q_st)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < PB_N_DISTS * 32; i += kRgThreads) {
+    const int k = i >> 5, l = i & 31;
+    uint32_t pos = 0, neg = 0;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(table + (size_t)k * d + 4 * (l + 32 * j)));
+      pos |= ((t.x > 0.f) | ((t.y > 0.f) << 1) | ((t.z > 0.f) << 2) | ((t.w > 0.f) << 3)) << (4 * j);
+      neg |= ((t.x < 0.f) | ((t.y < 0.f) << 1) | ((t.z < 0.f) << 2) | ((t.w < 0.f) << 3)) << (4 * j);
+    }
+    t_sign[i] = pos | (neg << 16);
+  }
+  if (threadIdx.x < 16) {
+    const uint32_t b = threadIdx.x;
+    mask_lut[b] = make_uint2(((b & 1u) ? 0xFFFFu : 0u) | ((b & 2u) ? 0xFFFF0000u : 0u),
+                             ((b & 4u) ? 0xFFFFu : 0u) | ((b & 8u) ? 0xFFFF0000u : 0u));
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t q_u32 = smem_u32(q_st), b_u32 = smem_u32(b_st);
+  const uint32_t bits_u32 = smem_u32(bits_ring);
+
+  if (warp == kRgWarps) {
+    // ================================================================== MMA issuer (as above)
+    if (lane == 0) {
+      for (int g = 0; g < n_total; ++g) {
+        const int st = g & (kTcStages - 1);
+        mbar_wait(full + st, (uint32_t)((g / kTcStages) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < kTcStageEdges / 16; ++ks) {
+          const uint64_t b_desc = make_smem_desc(b_u32 + st * kTcBStage + ks * 2048, kTcBStage, 1024);
+#pragma unroll
+          for (int mb = 0; mb < kMB; ++mb) {
+            const uint64_t a_desc = make_smem_desc(q_u32 + st * kQStage + 2 * mb * kChunkBytes + ks * 2048, kChunkBytes, 1024);
+            umma<true>(tmem_base + mb * kTcN, a_desc, b_desc, idesc, (g > 0 || ks > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty + st);
+      }
+      if (n_total > 0) umma_commit(done);
+    }
+  } else {
+    // ================================================================== gather warps (one source at a time)
+    const int last_pos = n_edges - 1;
+    uint32_t q_off[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int c4 = lane + 32 * j;
+      q_off[j] = (uint32_t)(c4 >> 4) * kChunkBytes + (uint32_t)(((c4 & 15) >> 1) << 4) + (uint32_t)(c4 & 1) * 8u;
+    }
+    // copy: lane moves the 16-byte units lane, lane + 32 (, ...) of a row = channels 8 k .. 8 k + 7 -> 64-channel block
+    // k / 8, unit k % 8 of the edge's line; unit k + 32 sits four blocks further
+    const uint32_t cp_off = (uint32_t)(lane >> 3) * kChunkBytes + (uint32_t)((lane & 7) << 4);
+    const uint32_t b_off = (uint32_t)((lane >> 2) << 4) + (uint32_t)(lane & 3) * 4u;
+    struct Hdr { uint2 x[CPL], root[CPL], res[CPL]; };
+    struct Meta { int u, deg, vep; };
+    auto load_meta = [&](int64_t vi) {
+      Meta m;
+      if (vi < r1) {
+        const int4 t = __ldg(visit_meta + vi);
+        m.u = t.x; m.deg = t.z; m.vep = __ldg(visit_edge_ptr + vi);
+      } else { m.u = 0; m.deg = 0; m.vep = 0; }
+      return m;
+    };
+    // records of edges c0 .. c0 + 31 of source vi (lane = edge): {row block of dH, kind | dist << 8, edge id, 1/|segment|}
+    auto load_rec = [&](int64_t vi, const Meta& m, int c0) {
+      return c0 + lane < m.deg ? __ldg(stream + 3 * vi + m.vep + 3 + c0 + lane) : make_int4(0, 0, 0, 0);
+    };
+    auto load_hdr = [&](Hdr& h, int u) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const size_t c4 = 4 * (size_t)(lane + 32 * j);
+        h.x[j] = __ldg(reinterpret_cast<const uint2*>(x + (size_t)u * d + c4));
+        h.root[j] = __ldg(reinterpret_cast<const uint2*>(d_a + ((size_t)u * (n_rel + 1) + n_rel) * d + c4));
+        h.res[j] = gy_res ? ld_stream2(gy_res + (size_t)u * d + c4) : make_uint2(0u, 0u);
+      }
+    };
+    int load_ok = -1;                                              // last stage index this warp knows to be free
+    // copies rows + keep bits of edges [0, n) of `rec` (n <= 32) into the slots of positions pbase ..; one cp.async group.
+    // Non-blocking mode gives up (false, nothing issued) when a stage still holds edges the tensor core has not read.
+    auto issue = [&](const int4& rec, int n, int pbase, bool blocking) -> bool {
+      if (n > 0) {
+        const int s_last = (pbase + n - 1) / kTcStageEdges;
+        for (int sx = max(pbase / kTcStageEdges, load_ok + 1); sx <= s_last; ++sx) {
+          uint64_t* bar = empty + (sx & (kTcStages - 1));
+          const uint32_t par = (uint32_t)(((sx / kTcStages) & 1) ^ 1);
+          if (blocking) mbar_wait_backoff(bar, par);
+          else if (!mbar_test(bar, par)) return false;
+          load_ok = sx;
+        }
+        for (int i = 0; i < n; ++i) {
+          const uint32_t rx = (uint32_t)__shfl_sync(kFull, rec.x, i);
+          const int p = pbase + i;
+          const int st = (p / kTcStageEdges) & (kTcStages - 1), slot = p & (kTcStageEdges - 1);
+          const uint32_t dst = q_u32 + st * kQStage + slot * 128 + (cp_off ^ ((uint32_t)(slot & 7) << 4));
+          const char* src = reinterpret_cast<const char*>(d_a) + (size_t)rx * kRow + 16 * lane;
+#pragma unroll
+          for (int h = 0; h < d / 256; ++h) cp_async16(dst + h * 4 * kChunkBytes, src + 512 * h);
+        }
+        if constexpr (DROPOUT) {
+          if (lane < n) {
+            const uint32_t dst = bits_u32 + (uint32_t)((pbase + lane) & (kRgSlots - 1)) * kBitsSlot;
+            const char* src = reinterpret_cast<const char*>(keep_bits) + (size_t)(uint32_t)rec.z * kBitsSlot;
+#pragma unroll
+            for (int q = 0; q < kBitsSlot / 16; ++q) cp_async16(dst + 16 * q, src + 16 * q);
+          }
+        }
+      }
+      cp_async_commit();
+      return true;
+    };
+
+    const int64_t v0 = r0 + warp;
+    Meta m0 = load_meta(v0), m1 = load_meta(v0 + kRgWarps), m2 = load_meta(v0 + 2 * kRgWarps), m3;
+    int4 rec_cur = load_rec(v0, m0, 0), rec_nxt = load_rec(v0 + kRgWarps, m1, 0), rec_nn;
+    Hdr hdr;
+    load_hdr(hdr, m0.u);
+    issue(rec_cur, min(m0.deg, 32), m0.vep - e0, true);
+    for (int64_t vi = v0; vi < r1; vi += kRgWarps) {
+      m3 = load_meta(vi + 3 * kRgWarps);
+      rec_nn = load_rec(vi + 2 * kRgWarps, m2, 0);
+      const int u = m0.u, deg = m0.deg;
+      const int pos0 = m0.vep - e0;
+      float4 xu[CPL], acc[CPL];
+      uint32_t xpos = 0, xneg = 0;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const float2 xa = unpack_bf16x2(hdr.x[j].x), xb = unpack_bf16x2(hdr.x[j].y);
+        xu[j] = make_float4(xa.x, xa.y, xb.x, xb.y);
+        const float2 ra = unpack_bf16x2(hdr.root[j].x), rb = unpack_bf16x2(hdr.root[j].y);
+        const float2 sa = unpack_bf16x2(hdr.res[j].x), sb2 = unpack_bf16x2(hdr.res[j].y);
+        acc[j] = make_float4(ra.x + sa.x, ra.y + sa.y, rb.x + sb2.x, rb.y + sb2.y);
+        const int bx = __float_as_int(xu[j].x), by = __float_as_int(xu[j].y), bz = __float_as_int(xu[j].z), bw = __float_as_int(xu[j].w);
+        xpos |= (uint32_t)((bx > 0) | ((by > 0) << 1) | ((bz > 0) << 2) | ((bw > 0) << 3)) << (4 * j);
+        xneg |= (uint32_t)(((uint32_t)bx > 0x80000000u) | (((uint32_t)by > 0x80000000u) << 1) | (((uint32_t)bz > 0x80000000u) << 2) |
+                           (((uint32_t)bw > 0x80000000u) << 3)) << (4 * j);
+      }
+      load_hdr(hdr, m1.u);                                         // next source's rows: in flight during this one
+      // next source's gradient rows: start them now if their stages are free, else after this source
+      const bool eager = issue(rec_nxt, min(m1.deg, 32), m1.vep - e0, false);
+      if (eager) cp_async_wait<1>(); else cp_async_wait<0>();      // this source's copies (every lane: its own part)
+      __syncwarp();
+      int pend_n = 0;
+      for (int c0 = 0; c0 < deg; c0 += 32) {
+        const int n = min(deg - c0, 32);
+        if (c0 > 0) {                                              // out-degree > 32: synchronous chunks
+          rec_cur = load_rec(vi, m0, c0);
+          issue(rec_cur, n, pos0 + c0, true);
+          cp_async_wait<0>();
+          __syncwarp();
+        }
+        for (int i = 0; i < n; ++i) {
+          const int p = pos0 + c0 + i;
+          const int st = (p / kTcStageEdges) & (kTcStages - 1), slot = p & (kTcStageEdges - 1);
+          const int dist = (__shfl_sync(kFull, rec_cur.y, i) >> 8) & (PB_N_DISTS - 1);
+          float coef = __int_as_float(__shfl_sync(kFull, rec_cur.w, i));
+          if constexpr (DROPOUT) coef *= keep_scale;
+          const uint32_t swz = (uint32_t)(slot & 7) << 4;
+          const uint32_t q_row = q_u32 + st * kQStage + slot * 128;
+          uint2 raw[CPL];
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) raw[j] = lds64(q_row + (q_off[j] ^ swz));
+          const float* trow = t_s + dist * d + 4 * lane;
+          const uint32_t ts = t_sign[dist * 32 + lane];
+          uint32_t keep = (xpos & ts) | (xneg & (ts >> 16));
+          if constexpr (DROPOUT) keep &= lds16(bits_u32 + (uint32_t)(p & (kRgSlots - 1)) * kBitsSlot + 2 * lane);
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) {
+            const uint2 mk = mask_lut[(keep >> (4 * j)) & 15u];
+            const float2 da = unpack_bf16x2(raw[j].x & mk.x), db = unpack_bf16x2(raw[j].y & mk.y);
+            const float4 ds = make_float4(da.x * coef, da.y * coef, db.x * coef, db.y * coef);
+            const float4 t = *reinterpret_cast<const float4*>(trow + 128 * j);
+            const float4 xv = xu[j];
+            acc[j].x += ds.x * t.x; acc[j].y += ds.y * t.y; acc[j].z += ds.z * t.z; acc[j].w += ds.w * t.w;
+            sts64(q_row + (q_off[j] ^ swz), pack_bf16x2(ds.x * xv.x, ds.y * xv.y), pack_bf16x2(ds.z * xv.z, ds.w * xv.w));
+          }
+          if (lane < 16) {
+            const uint32_t v = (dist == 2 * lane ? 0x3F80u : 0u) | (dist == 2 * lane + 1 ? 0x3F800000u : 0u);
+            sts32(b_u32 + st * kTcBStage + slot * 128 + (b_off ^ swz), v);
+          }
+          ++pend_n;
+          const bool tail = p == last_pos && slot != kTcStageEdges - 1;
+          if (c0 + i + 1 == deg || slot == kTcStageEdges - 1 || tail) {       // warp-uniform
+            if (tail) {
+              for (int k = slot + 1; k < kTcStageEdges; ++k)
+                if (lane < 16) sts32(b_u32 + st * kTcBStage + k * 128 + (b_off ^ ((uint32_t)(k & 7) << 4)), 0u);
+              pend_n += kTcStageEdges - 1 - slot;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_n(full + st, (uint32_t)pend_n);
+            pend_n = 0;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        st_stream2(gx + (size_t)u * d + 4 * (lane + 32 * j),
+                   make_uint2(pack_bf16x2(acc[j].x, acc[j].y), pack_bf16x2(acc[j].z, acc[j].w)));
+      if (!eager) issue(rec_nxt, min(m1.deg, 32), m1.vep - e0, true);
+      m0 = m1; m1 = m2; m2 = m3;
+      rec_cur = rec_nxt; rec_nxt = rec_nn;
+    }
+    cp_async_wait<0>();
+    // ================================================================== epilogue: TMEM -> partials [cta][32][d]
+    if (warp < 4) {
+      if (n_total > 0) {
+        mbar_wait(done, 0);
+        tc_fence_after();
+      }
+      float* out = partials + (size_t)blockIdx.x * PB_N_DISTS * d;
+#pragma unroll 1
+      for (int mb = 0; mb < kMB; ++mb) {
+        uint32_t v[32];
+        if (n_total > 0) {
+          tmem_ld_32x32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)(mb * kTcN), v);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) v[k] = 0u;
+        }
+        const int c = mb * 128 + 32 * warp + lane;
+#pragma unroll
+        for (int k = 0; k < PB_N_DISTS; ++k) out[(size_t)k * d + c] = __uint_as_float(v[k]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kRgWarps) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kMB * kTcN < 32 ? 32 : kMB * kTcN);
+  }
+}
+
+static size_t rg_smem_bytes(int d) {
+  const int g16 = (d / 128 + 3) / 4;
+  return (size_t)kTcStages * ((size_t)(d / 64) * kTcStageEdges * 128 + kTcBStage) + (size_t)PB_N_DISTS * d * sizeof(float) +
+         PB_N_DISTS * 32 * sizeof(uint32_t) + 128 /*mask LUT*/ + (size_t)kRgSlots * (g16 * 64) /*keep bits*/ +
+         256 /*barriers, TMEM slot*/ + 1024 /*alignment*/;
+}
+
+template <bool DROP, int CPL>
+static int launch_ring(const pb_csr_t* g, const void* x, const float* table, const void* d_a, const void* gy_res, void* gx,
+                       float* partials, const uint16_t* bits, float scale, cudaStream_t st) {
+  const int d = 128 * CPL;
+  const size_t smem = rg_smem_bytes(d);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    PB_CUDA(cudaFuncSetAttribute(agg_bwd_ring_kernel<DROP, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  const uint32_t idesc = make_idesc(true, 128, kTcN, 1, 1);
+  agg_bwd_ring_kernel<DROP, CPL><<<agg_bwd_tc_ctas(g->n_nodes), kRgThreads, smem, st>>>(
+      reinterpret_cast<const int4*>(g->visit_meta), g->visit_edge_ptr, reinterpret_cast<const int4*>(g->bwd_stream),
+      static_cast<const __nv_bfloat16*>(x), table, static_cast<const __nv_bfloat16*>(d_a),
+      static_cast<const __nv_bfloat16*>(gy_res), static_cast<__nv_bfloat16*>(gx), partials, g->n_nodes, g->n_relations, bits,
+      scale, idesc);
+  PB_LAUNCH_CHECK();
+  return PB_OK;
+}
+
+// PB200_AGG_BWD_RING=0 keeps the register-gather kernel (A/B measurements)
+static bool ring_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PB200_AGG_BWD_RING");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static size_t tc_smem_bytes(int d) {
   return (size_t)kTcStages * ((size_t)(d / 64) * kTcStageEdges * 128 + kTcBStage) + (size_t)PB_N_DISTS * d * sizeof(float) +
          PB_N_DISTS * 32 * sizeof(uint32_t) /*sign masks*/ + 128 /*mask LUT*/ + 256 /*barriers*/ + 1024 /*alignment*/;
@@ -410,6 +783,12 @@ static int launch_tc(const pb_csr_t* g, const void* x, const float* table, const
 int agg_bwd_tc_launch(const pb_csr_t* g, const void* x, int d, const float* table, const void* d_a, int64_t ldda,
                       const void* gy_res, void* gx, float* partials, const uint16_t* bits, float scale, bool act_bf16,
                       cudaStream_t st) {
+  if (act_bf16 && g->bwd_stream && ldda == (int64_t)(g->n_relations + 1) * d && ring_enabled()) {
+    if (d == 512) return bits ? launch_ring<true, 4>(g, x, table, d_a, gy_res, gx, partials, bits, scale, st)
+                              : launch_ring<false, 4>(g, x, table, d_a, gy_res, gx, partials, bits, scale, st);
+    return bits ? launch_ring<true, 2>(g, x, table, d_a, gy_res, gx, partials, bits, scale, st)
+                : launch_ring<false, 2>(g, x, table, d_a, gy_res, gx, partials, bits, scale, st);
+  }
 #define PB_TC(DR, CPL, AB) launch_tc<DR, CPL, AB>(g, x, table, d_a, ldda, gy_res, gx, partials, bits, scale, st)
 #define PB_TC_D(DR, AB) (d == 512 ? PB_TC(DR, 4, AB) : PB_TC(DR, 2, AB))
   if (act_bf16) return bits ? PB_TC_D(true, true) : PB_TC_D(false, true);

@@ -408,7 +408,6 @@ __global__ void __launch_bounds__(kQThreads) dist_reduce_kernel(const void* __re
 // registers: slot s of the ring is consumed (record p) and immediately refilled with the row of record p + kRing.
 // The ring is indexed statically (the trip over its slots is fully unrolled), so nothing is spilled or rotated.
 constexpr int kRing = 16;
-enum : int { kRecEdge = 0, kRecX = 1, kRecRoot = 2, kRecRes = 3, kRecNop = 4, kRecLast = 8 };
 
 template <int W> struct RawW { uint32_t w[W]; };
 template <int W>

@@ -45,6 +45,9 @@ int agg_bwd_tc_launch(const pb_csr_t* g, const void* x, int d, const float* tabl
                       const void* gy_res, void* gx, float* partials, const uint16_t* bits, float scale, bool act_bf16,
                       cudaStream_t st);
 
+// record kinds of the fused backward's stream (pb_csr_bwd_stream; layout next to bwd_stream_kernel in aggregate.cu)
+enum : int { kRecEdge = 0, kRecX = 1, kRecRoot = 2, kRecRes = 3, kRecNop = 4, kRecLast = 8 };
+
 // ------------------------------------------------------------------ device helpers
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 

@@ -97,6 +97,7 @@ class LayerConfig:
     training: bool
     batch_norm: bool           # fuse BN + ReLU + residual (GCN layer) or return the raw GCL output
     save_operand: bool = False  # keep the aggregated GEMM operand for backward instead of recomputing it
+    keep_bits: object = None    # (bits, ready event) drawn ahead of the call by prefetch_keep_bits, else None
     eps: float = BN_EPS
     momentum: float = BN_MOMENTUM
 
@@ -139,6 +140,36 @@ def _keep_bits(n_edges: int, d: int, p: float, seed: int, dev, st: int):
     return bits
 
 
+_bits_prefetch = os.environ.get("PB200_BITS_PREFETCH", "1") != "0"
+_bits_streams = {}
+
+
+def prefetch_keep_bits(plan: CsrPlan, d: int, p: float, n_calls: int):
+    """Draws the keep-bits of the next ``n_calls`` layer calls of a stack (same seeds, same order as the calls would
+    draw them) on a side stream: pb_dropout_bits is pure integer arithmetic on no input, so it fills issue slots the
+    tensor-core- and HBM-bound kernels of the preceding layers leave idle instead of sitting between them.
+    Returns [(seed, (bits, ready_event))] or None when there is nothing to draw."""
+    if not _bits_prefetch or p <= 0.0 or plan.n_edges == 0 or n_calls <= 0:
+        return None
+    dev = plan.device
+    side = _bits_streams.get(dev)
+    if side is None:
+        side = _bits_streams[dev] = torch.cuda.Stream(device=dev)
+    nbytes = _ffi.lib().pb_dropout_bits_bytes(plan.n_edges, d)
+    main = torch.cuda.current_stream(dev)
+    seeds = [next_seed() for _ in range(n_calls)]
+    bufs = [torch.empty(nbytes // 2, dtype=torch.int16, device=dev) for _ in range(n_calls)]   # owned by `main`
+    side.wait_stream(main)               # the buffers' previous users on `main` are done before the side stream writes
+    out = []
+    with torch.cuda.device(dev):
+        for seed, bits in zip(seeds, bufs):
+            _call("pb_dropout_bits", plan.n_edges, d, float(p), int(seed), bits.data_ptr(), side.cuda_stream)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            out.append((seed, (bits, ev)))
+    return out
+
+
 class RGCLayerFn(torch.autograd.Function):
     """y = x_res + relu(BN(GCL(x)))   (cfg.batch_norm)   or   y = GCL(x)   (plain layer)."""
 
@@ -172,7 +203,12 @@ class RGCLayerFn(torch.autograd.Function):
             table = _edge_table(nn_w, nn_b, d, st)
             a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
             p = cfg.p_drop if cfg.training else 0.0
-            keep_bits = _keep_bits(plan.n_edges, d, p, cfg.seed, dev, st)
+            if cfg.keep_bits is not None and p > 0.0:
+                keep_bits, ready = cfg.keep_bits
+                torch.cuda.current_stream(dev).wait_event(ready)
+            else:
+                keep_bits = _keep_bits(plan.n_edges, d, p, cfg.seed, dev, st)
+            cfg.keep_bits = None
             _call("pb_agg_fwd", plan.ref(), x.data_ptr(), d, table.data_ptr(), a_hi.data_ptr(), _ffi.ptr(a_lo), k,
                   cfg.dtype, _ffi.ptr(keep_bits), p, act, st)
             ctx.keep_bits = keep_bits
@@ -313,7 +349,7 @@ SAVE_OPERAND_MAX_BYTES = int(os.environ.get("PB200_SAVE_OPERAND_MB", "2048")) <<
 def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, beta=None, running_mean=None,
               running_var=None, batch_norm: bool, training: bool, p_drop: float, precision: Optional[str] = None,
               seed: Optional[int] = None, eps: float = BN_EPS, momentum: float = BN_MOMENTUM,
-              save_operand: Optional[bool] = None, struct=None):
+              save_operand: Optional[bool] = None, struct=None, keep_bits=None):
     dtype = _PRECISIONS[precision or _default_precision]
     if save_operand is None:
         elem = 2 if dtype == _ffi.PB_BF16 else 8
@@ -322,7 +358,7 @@ def rgc_layer(x, weight, root, bias, nn_w, nn_b, plan: CsrPlan, *, gamma=None, b
     cfg = LayerConfig(dtype=dtype, p_drop=float(p_drop),
                       seed=next_seed() if seed is None else int(seed), training=bool(training),
                       batch_norm=bool(batch_norm), save_operand=bool(save_operand), eps=float(eps),
-                      momentum=float(momentum))
+                      momentum=float(momentum), keep_bits=keep_bits)
     return RGCLayerFn.apply(x, weight, root, bias, nn_w, nn_b, gamma, beta, running_mean, running_var, plan, cfg,
                             struct)
 

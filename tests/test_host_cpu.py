@@ -254,25 +254,3 @@ def test_batched_bn_tables_match_per_table_path():
     for k in sa:
         if "running" in k or "num_batches" in k:
             torch.testing.assert_close(sa[k].float(), sb[k].float(), rtol=1e-5, atol=1e-6, msg=k)
-
-
-def test_row_scatter_gather_gradients():
-    """ops.ScatterRowsFn / GatherRowsFn (injective node -> padded-row map of the structured layout): values and
-    gradients equal autograd's index_copy / index_select formulation."""
-    from polyphemus_b200 import ops
-
-    gen = torch.Generator().manual_seed(0)
-    n, n_rows, d = 37, 64, 8
-    pos = torch.randperm(n_rows, generator=gen)[:n]
-    x = torch.randn(n, d, generator=gen, requires_grad=True)
-    x_ref = x.detach().clone().requires_grad_(True)
-    g = torch.randn(n, d, generator=gen)
-    w = torch.randn(n_rows, d, generator=gen)
-    xp = ops.ScatterRowsFn.apply(x, pos, n_rows)
-    y = ops.GatherRowsFn.apply(xp * w, pos)
-    y.backward(g)
-    xp_ref = torch.zeros(n_rows, d).index_copy(0, pos, x_ref)
-    y_ref = (xp_ref * w).index_select(0, pos)
-    y_ref.backward(g)
-    assert torch.equal(xp, xp_ref) and torch.equal(y, y_ref)
-    torch.testing.assert_close(x.grad, x_ref.grad, rtol=0, atol=0)

@@ -708,6 +708,31 @@ def test_bar_expand_and_segment_sum(cuda, d):
     torch.testing.assert_close(z_dev.grad.cpu().double(), ref, rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_row_scatter_gather_gradients(cuda, out_dtype):
+    """ops.ScatterRowsFn / GatherRowsFn (pb_rows_scatter / pb_rows_gather: node -> padded row of the structured layout,
+    injective, storage conversion fused): values and gradients equal autograd's index_copy / index_select formulation
+    on a real structured plan, padding rows zero."""
+    from polyphemus_b200 import ops
+
+    g, _ = _graph(cuda, bsz=5, n_bars=2, p=0.35, seed=7)
+    st_ = g.structured
+    n, n_rows, d = g.num_nodes, st_.n_padded, 64
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(n, d, generator=gen).to(cuda).requires_grad_(True)
+    x_ref = x.detach().clone().requires_grad_(True)
+    g_out = torch.randn(n, d, generator=gen).to(cuda)
+    w = torch.randn(n_rows, d, generator=gen).to(cuda)
+    xp = ops.ScatterRowsFn.apply(x, st_, out_dtype)
+    y = ops.GatherRowsFn.apply(xp * w.to(out_dtype), st_, torch.float32)
+    y.backward(g_out)
+    xp_ref = torch.zeros(n_rows, d, device=cuda).index_copy(0, st_.pos, x_ref).to(out_dtype)
+    y_ref = (xp_ref * w.to(out_dtype)).index_select(0, st_.pos).float()
+    y_ref.backward(g_out)
+    assert xp.dtype == out_dtype and torch.equal(xp, xp_ref) and torch.equal(y, y_ref)
+    torch.testing.assert_close(x.grad, x_ref.grad, rtol=0, atol=0)
+
+
 def test_token_hist_matches_bincount(cuda):
     """pb_token_hist == per-set bincount of the (pitch, duration) ids of slots 1..15 (the histogram that weights the
     BatchNorm statistics of the folded embedding tables, model.py:355-376), incl. a batch without drum nodes."""
