@@ -411,6 +411,22 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
   return v;
 }
+// read-only tables (written once before the CTA-wide barrier): not volatile, the compiler may schedule them freely
+__device__ __forceinline__ uint32_t lds32_ro(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64_ro(uint32_t addr) {
+  uint2 v;
+  asm("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f_ro(uint32_t addr) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
   uint16_t v;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
@@ -495,13 +511,14 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t q_u32 = smem_u32(q_st), b_u32 = smem_u32(b_st);
   const uint32_t bits_u32 = smem_u32(bits_ring);
+  const uint32_t trow_u32 = smem_u32(t_s) + 16 * lane, sign_u32 = smem_u32(t_sign) + 4 * lane, lut_u32 = smem_u32(mask_lut);
 
   if (warp == kRgWarps) {
     // ================================================================== MMA issuer (as above)
     if (lane == 0) {
       for (int g = 0; g < n_total; ++g) {
         const int st = g & (kTcStages - 1);
-        mbar_wait(full + st, (uint32_t)((g / kTcStages) & 1));
+        mbar_wait_backoff(full + st, (uint32_t)((g / kTcStages) & 1));
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < kTcStageEdges / 16; ++ks) {
@@ -637,16 +654,16 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
           uint2 raw[CPL];
 #pragma unroll
           for (int j = 0; j < CPL; ++j) raw[j] = lds64(q_row + (q_off[j] ^ swz));
-          const float* trow = t_s + dist * d + 4 * lane;
-          const uint32_t ts = t_sign[dist * 32 + lane];
+          const uint32_t trow = trow_u32 + dist * (d * 4);
+          const uint32_t ts = lds32_ro(sign_u32 + dist * 128);
           uint32_t keep = (xpos & ts) | (xneg & (ts >> 16));
           if constexpr (DROPOUT) keep &= lds16(bits_u32 + (uint32_t)(p & (kRgSlots - 1)) * kBitsSlot + 2 * lane);
 #pragma unroll
           for (int j = 0; j < CPL; ++j) {
-            const uint2 mk = mask_lut[(keep >> (4 * j)) & 15u];
+            const uint2 mk = lds64_ro(lut_u32 + (j == 0 ? (keep << 3) & 0x78u : (keep >> (4 * j - 3)) & 0x78u));
             const float2 da = unpack_bf16x2(raw[j].x & mk.x), db = unpack_bf16x2(raw[j].y & mk.y);
             const float4 ds = make_float4(da.x * coef, da.y * coef, db.x * coef, db.y * coef);
-            const float4 t = *reinterpret_cast<const float4*>(trow + 128 * j);
+            const float4 t = lds128f_ro(trow + 512 * j);
             const float4 xv = xu[j];
             acc[j].x += ds.x * t.x; acc[j].y += ds.y * t.y; acc[j].z += ds.z * t.z; acc[j].w += ds.w * t.w;
             sts64(q_row + (q_off[j] ^ swz), pack_bf16x2(ds.x * xv.x, ds.y * xv.y), pack_bf16x2(ds.z * xv.z, ds.w * xv.w));

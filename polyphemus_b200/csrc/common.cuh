@@ -78,8 +78,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));   // exact: bf16 = top half of fp32
 }
 
 // ------------------------------------------------------------------ activation storage (fp32 or bf16 rows)
