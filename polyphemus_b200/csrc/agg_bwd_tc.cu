@@ -518,7 +518,11 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
     if (lane == 0) {
       for (int g = 0; g < n_total; ++g) {
         const int st = g & (kTcStages - 1);
+#ifdef PB_RG_MMA_SPIN
+        mbar_wait(full + st, (uint32_t)((g / kTcStages) & 1));
+#else
         mbar_wait_backoff(full + st, (uint32_t)((g / kTcStages) & 1));
+#endif
         tc_fence_after();
 #pragma unroll
         for (int ks = 0; ks < kTcStageEdges / 16; ++ks) {

@@ -217,6 +217,154 @@ __global__ void __launch_bounds__(256) agg_fwd_kernel(const int* __restrict__ in
   }
 }
 
+// Pipelined forward for d = 128 * CPL <= 512 on plans with visit_meta. The kernel above walks, per node, a chain of
+// dependent loads (node_order -> in_ptr -> in_edge -> rows: four L2 round trips of ~0.7 us with one row in flight per
+// warp), which is what bounds it (28 KB in flight per SM ~ 4 TB/s). Here a persistent warp keeps the chain of the next
+// two nodes in flight (metadata two nodes ahead, segment offsets + edge records one node ahead) and the rows of the
+// next in-edge in registers while it consumes the current one. GCL.message's dropout is applied to the raw feature
+// words (AND with a mask from a 16-entry shared-memory table: 5 instructions per 4 channels instead of 16); a dropped
+// channel is an exact +0 from there on.
+#ifndef PB_FWD_PIPE_CTAS
+#define PB_FWD_PIPE_CTAS 3
+#endif
+template <bool ABF> struct XRaw { using type = float4; };
+template <> struct XRaw<true> { using type = uint2; };
+
+template <bool BF16, bool DROPOUT, int CPL, bool ABF>
+__global__ void __launch_bounds__(256) agg_fwd_pipe_kernel(const int4* __restrict__ visit_meta, const int* __restrict__ in_ptr,
+                                                           const int* __restrict__ in_edge, const int* __restrict__ in_eid,
+                                                           const void* __restrict__ x, const float* __restrict__ table,
+                                                           void* __restrict__ a_hi, void* __restrict__ a_lo, int64_t lda,
+                                                           int64_t n_nodes, int n_rel, int n_edges,
+                                                           const uint16_t* __restrict__ keep_bits, float keep_scale) {
+  constexpr uint32_t kFull = 0xffffffffu;
+  constexpr int d = 128 * CPL;
+  static_assert(CPL <= 4, "one keep-bit word per lane");
+  using Raw = typename XRaw<ABF>::type;
+  __shared__ uint4 lut[16];                                  // 4 keep bits -> AND masks (bf16: .x/.y pairs, fp32: 4 words)
+  if (threadIdx.x < 16) {
+    const uint32_t b = threadIdx.x;
+    if constexpr (ABF)
+      lut[b] = make_uint4(((b & 1u) ? 0xFFFFu : 0u) | ((b & 2u) ? 0xFFFF0000u : 0u),
+                          ((b & 4u) ? 0xFFFFu : 0u) | ((b & 8u) ? 0xFFFF0000u : 0u), 0u, 0u);
+    else
+      lut[b] = make_uint4((b & 1u) ? ~0u : 0u, (b & 2u) ? ~0u : 0u, (b & 4u) ? ~0u : 0u, (b & 8u) ? ~0u : 0u);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  struct Recs { int ptr; uint32_t pk, eid; };
+  auto load_meta = [&](int64_t vi) { return vi < n_nodes ? __ldg(visit_meta + vi) : make_int4(0, 0, 0, 0); };
+  // segment offsets of the node (lanes 0..n_rel) and its first 32 in-edge records (reading past the node's last edge
+  // is harmless: the index is clamped to the array, the values are never used)
+  auto load_recs = [&](const int4& m) {
+    Recs r;
+    r.ptr = lane <= n_rel ? __ldg(in_ptr + (int64_t)m.x * n_rel + lane) : 0;
+    const int i = min(m.w + lane, n_edges - 1);
+    r.pk = (uint32_t)__ldg(in_edge + i);
+    r.eid = 0;
+    if constexpr (DROPOUT) r.eid = (uint32_t)__ldg(in_eid + i);
+    return r;
+  };
+  auto ld_row = [&](Raw (&raw)[CPL], size_t elem) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      if constexpr (ABF) raw[j] = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x) + elem + 128 * j));
+      else raw[j] = ldg4(static_cast<const float*>(x) + elem + 128 * j);
+    }
+  };
+  auto unpack = [&](const Raw& r) {
+    if constexpr (ABF) {
+      const float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y);
+      return make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      return r;
+    }
+  };
+  int4 m_cur = load_meta(w0), m_nxt = load_meta(w0 + n_warps), m_nn;
+  Recs rc = load_recs(m_cur), rn;
+  for (int64_t vi = w0; vi < n_nodes; vi += n_warps) {
+    m_nn = load_meta(vi + 2 * n_warps);
+    rn = load_recs(m_nxt);
+    const int64_t v = m_cur.x;
+    const size_t row = (size_t)v * lda;
+    const int beg_all = m_cur.w;
+    const int end_all = __shfl_sync(kFull, rc.ptr, n_rel);
+    int base = beg_all;
+    uint32_t my_pk = rc.pk, my_eid = rc.eid;
+    Raw ra[CPL], rb[CPL];
+    uint32_t pka = 0, pkb = 0, kwa = 0, kwb = 0;
+    auto fetch = [&](Raw (&raw)[CPL], uint32_t& pk, uint32_t& kw, int e) {
+      if (e - base == 32) {  // warp-uniform: next batch of records (in-degree > 32 only)
+        base = e;
+        const int i = min(base + lane, n_edges - 1);
+        my_pk = (uint32_t)__ldg(in_edge + i);
+        if constexpr (DROPOUT) my_eid = (uint32_t)__ldg(in_eid + i);
+      }
+      pk = __shfl_sync(kFull, my_pk, e - base);
+      ld_row(raw, (size_t)(pk & 0x03FFFFFFu) * d + 4 * lane);
+      if constexpr (DROPOUT) {
+        const uint32_t eid = __shfl_sync(kFull, my_eid, e - base);
+        kw = __ldg(keep_bits + (size_t)eid * 32 + lane);
+      }
+    };
+    if (beg_all < end_all) fetch(ra, pka, kwa, beg_all);
+    // root block: the node's own features, converted to the operand dtype
+    {
+      Raw rr[CPL];
+      ld_row(rr, (size_t)v * d + 4 * lane);
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+        store_operand<BF16>(a_hi, a_lo, row + (size_t)n_rel * d + 4 * (lane + 32 * j), unpack(rr[j]));
+    }
+    int e = beg_all;
+    for (int r = 0; r < n_rel; ++r) {
+      const int seg_end = __shfl_sync(kFull, rc.ptr, r + 1);
+      const int cnt = seg_end - e;
+      float4 acc[CPL];
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (; e < seg_end; ++e) {
+        if (e + 1 < end_all) fetch(rb, pkb, kwb, e + 1);           // next in-edge (of any segment) in flight
+        const float* trow = table + (size_t)(pka >> 26) * d + 4 * lane;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+          Raw xr = ra[j];
+          if constexpr (DROPOUT) {
+            const uint4 mk = lut[(kwa >> (4 * j)) & 15u];
+            if constexpr (ABF) { xr.x &= mk.x; xr.y &= mk.y; }
+            else {
+              xr.x = __uint_as_float(__float_as_uint(xr.x) & mk.x); xr.y = __uint_as_float(__float_as_uint(xr.y) & mk.y);
+              xr.z = __uint_as_float(__float_as_uint(xr.z) & mk.z); xr.w = __uint_as_float(__float_as_uint(xr.w) & mk.w);
+            }
+          }
+          const float4 xs = unpack(xr);
+          const float4 t = ldg4(trow + 128 * j);
+          const float4 m = make_float4(fmaxf(xs.x * t.x, 0.f), fmaxf(xs.y * t.y, 0.f), fmaxf(xs.z * t.z, 0.f),
+                                       fmaxf(xs.w * t.w, 0.f));
+          if constexpr (DROPOUT) {
+            acc[j].x = fmaf(m.x, keep_scale, acc[j].x); acc[j].y = fmaf(m.y, keep_scale, acc[j].y);
+            acc[j].z = fmaf(m.z, keep_scale, acc[j].z); acc[j].w = fmaf(m.w, keep_scale, acc[j].w);
+          } else {
+            acc[j].x += m.x; acc[j].y += m.y; acc[j].z += m.z; acc[j].w += m.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) ra[j] = rb[j];
+        pka = pkb; kwa = kwb;
+      }
+      const float inv = cnt > 1 ? 1.0f / (float)cnt : 1.0f;
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        const float4 h = make_float4(acc[j].x * inv, acc[j].y * inv, acc[j].z * inv, acc[j].w * inv);
+        store_operand<BF16>(a_hi, a_lo, row + (size_t)r * d + 4 * (lane + 32 * j), h);
+      }
+    }
+    m_cur = m_nxt; m_nxt = m_nn; rc = rn;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- backward
 template <bool BF16>
 __device__ __forceinline__ float4 load_grad4(const void* d_a, size_t elem_off) {
@@ -697,12 +845,36 @@ extern "C" int pb_dropout_bits(int64_t n_edges, int32_t d, float p_drop, uint64_
   return PB_OK;
 }
 
+// PB200_AGG_FWD_PIPE=0 keeps the unpipelined forward (A/B measurements)
+static bool fwd_pipe_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PB200_AGG_FWD_PIPE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <bool BF16, bool DROP, bool ABF>
 static int launch_agg_fwd(const pb_csr_t* g, const void* x, int d, const float* table, void* a_hi, void* a_lo,
                           int64_t lda, const uint16_t* bits, float scale, cudaStream_t st) {
   const int cpl = (d + 127) / 128;
   const bool exact = d % 128 == 0 && (cpl == 1 || cpl == 2 || cpl == 4 || cpl == 8);
   const int threads = 256;
+  if (exact && cpl <= 4 && g->visit_meta && g->n_edges > 0 && fwd_pipe_enabled()) {
+    const int64_t want_p = (g->n_nodes * 32 + threads - 1) / threads;
+    const unsigned grid_p = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want_p, (int64_t)sm_count() * PB_FWD_PIPE_CTAS));
+#define PB_AGG_PIPE(CPL)                                                                                            \
+  agg_fwd_pipe_kernel<BF16, DROP, CPL, ABF><<<grid_p, threads, 0, st>>>(                                             \
+      reinterpret_cast<const int4*>(g->visit_meta), g->in_ptr, g->in_edge, g->in_eid, x, table, a_hi, a_lo, lda, g->n_nodes, \
+      g->n_relations, (int)g->n_edges, bits, scale)
+    if (cpl == 1) PB_AGG_PIPE(1);
+    else if (cpl == 2) PB_AGG_PIPE(2);
+    else PB_AGG_PIPE(4);
+#undef PB_AGG_PIPE
+    PB_LAUNCH_CHECK();
+    return PB_OK;
+  }
   const int64_t want = (g->n_nodes * 32 + threads - 1) / threads;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count() * 8 * 4));
 #define PB_AGG_FWD(CPL, EX)                                                                                      \
