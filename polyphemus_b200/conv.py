@@ -155,7 +155,10 @@ class GCN(nn.Module):
                 self.norm_layers.append(BatchNorm(hidden_dim))
         self.p = dropout
 
-    def forward(self, data):
+    def forward(self, data, out_perm: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.float32):
+        """``out_perm`` (int64 permutation of the nodes) returns the rows in that order, ``out_dtype`` in that storage
+        type — both folded into the structured layout's exit gather (the content decoder wants drum nodes first and
+        bf16 rows for its un-embedding GEMM)."""
         x = data.x
         st = data.structured if isinstance(data, Graph) and ops.structured_enabled() else None
         if st is not None and self.batch_norm and self.p == 0 and x.size(1) % 256 == 0 and x.is_cuda:
@@ -172,7 +175,8 @@ class GCN(nn.Module):
             for i, layer in enumerate(self.layers):
                 xp = layer(xp, plan=st.plan, bn=self.norm_layers[i].module, struct=st,
                            drawn=None if drawn is None else drawn[i])
-            return ops.GatherRowsFn.apply(xp, st, torch.float32)
+            rows = st if out_perm is None else _PermutedRows(st, out_perm)
+            return ops.GatherRowsFn.apply(xp, rows, out_dtype if act_bf16 else torch.float32)
         plan = plan_for(data, num_nodes=x.size(0))
         for i, layer in enumerate(self.layers):
             residual = x
@@ -184,7 +188,15 @@ class GCN(nn.Module):
                 if self.batch_norm:
                     h = self.norm_layers[i].module(h)
                 x = residual + F.relu(h)
-        return x
+        return x if out_perm is None else x.index_select(0, out_perm)
+
+
+class _PermutedRows:
+    """The structured layout's node -> padded-row map composed with a node permutation (row i <- node perm[i])."""
+
+    def __init__(self, st, perm: torch.Tensor):
+        self.pos = st.pos.index_select(0, perm)
+        self.n_padded, self.groups_ref = st.n_padded, st.groups_ref
 
 
 __all__ = ["GCL", "GCN", "BatchNorm", "Graph"]

@@ -49,6 +49,14 @@ def structured_enabled() -> bool:
     return _structured
 
 
+# content decoder: un-embed drum rows and the others separately (each with its own pitch head) when only the loss is needed
+_split_heads = os.environ.get("PB200_SPLIT_HEADS", "1") != "0"
+
+
+def split_heads_enabled() -> bool:
+    return _split_heads
+
+
 _bf16_activations = os.environ.get("PB200_BF16_ACT", "1") != "0"
 # "fused" (default): scatter-by-source and the edge-table gradient in one pass, shared-memory accumulators with
 # thread-owned columns; "legacy": the round-1 pair of kernels with the E x d intermediate (kept for A/B measurements)
@@ -426,6 +434,75 @@ class TensorCoreLinearFn(torch.autograd.Function):
                       dw.data_ptr(), m, k, n, None, dtype, ws.data_ptr(), ws_bytes, st, tag="linear")
         db = g.sum(0, dtype=torch.float32) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return dx, dw, db, None, None
+
+
+class SplitRowsLinearFn(torch.autograd.Function):
+    """Two Linears over the two row blocks of one matrix: rows [0, n0) of x go through (w0, b0), the rest through
+    (w1, b1); both share the contraction width. Used by the content decoder's un-embedding (drum rows first, then the
+    others: each row only gets the pitch head of its own instrument class). One input-gradient buffer is written by
+    both blocks (no per-slice zero-fill + add in autograd), weight gradients by the split-K kernel."""
+
+    @staticmethod
+    def forward(ctx, x, n0: int, w0, b0, w1, b1, dtype: int, out_bf16: bool):
+        m, k = x.shape
+        dev = x.device
+        x_hi, x_lo = _as_operand(x, dtype)
+        out_bf16 = bool(out_bf16 and dtype == _ffi.PB_BF16)
+        odt = torch.bfloat16 if out_bf16 else torch.float32
+        esz = x_hi.element_size()
+        outs, saved_w = [], []
+        with torch.cuda.device(dev):
+            for r0, rows, w, b in ((0, n0, w0, b0), (n0, m - n0, w1, b1)):
+                n = w.shape[0]
+                out = torch.empty((rows, n), dtype=odt, device=dev)
+                if rows > 0:
+                    w_hi, w_lo = _as_operand(w, dtype)
+                    bias_f = b.float().contiguous()
+                    _call("pb_gemm_nt", x_hi.data_ptr() + r0 * k * esz, None if x_lo is None else x_lo.data_ptr() + r0 * k * esz,
+                          k, w_hi.data_ptr(), _ffi.ptr(w_lo), k, bias_f.data_ptr(), out.data_ptr(), n, rows, n, k, dtype,
+                          int(out_bf16), _ffi.stream(), tag="linear")
+                outs.append(out)
+        ctx.save_for_backward(x_hi, x_lo, w0, w1)
+        ctx.dtype, ctx.n0, ctx.x_dtype = dtype, n0, x.dtype
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        x_hi, x_lo, w0, w1 = ctx.saved_tensors
+        dtype, n0 = ctx.dtype, ctx.n0
+        m, k = x_hi.shape
+        dev = x_hi.device
+        lib = _ffi.lib()
+        esz = x_hi.element_size()
+        dx_bf16 = dtype == _ffi.PB_BF16 and ctx.x_dtype == torch.bfloat16
+        dx = torch.empty((m, k), dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev)
+        grads = []
+        with torch.cuda.device(dev):
+            st = _ffi.stream()
+            for r0, rows, w, g in ((0, n0, w0, g0), (n0, m - n0, w1, g1)):
+                n = w.shape[0]
+                if rows == 0 or g is None:
+                    dx[r0:r0 + rows].zero_()
+                    grads += [torch.zeros_like(w), torch.zeros(n, dtype=torch.float32, device=dev)]
+                    continue
+                g_hi, g_lo = _as_operand(g, dtype)
+                wt_hi, wt_lo = _as_operand(w.t(), dtype)
+                _call("pb_gemm_nt", g_hi.data_ptr(), _ffi.ptr(g_lo), n, wt_hi.data_ptr(), _ffi.ptr(wt_lo), n, None,
+                      dx.data_ptr() + r0 * k * dx.element_size(), k, rows, k, n, dtype, int(dx_bf16), st, tag="linear")
+                dw = torch.empty((n, k), dtype=torch.float32, device=dev)
+                ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(rows, k, n, dtype)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                _call("pb_rgcn_gemm_bwd_weight", g_hi.data_ptr(), _ffi.ptr(g_lo), n, x_hi.data_ptr() + r0 * k * esz,
+                      None if x_lo is None else x_lo.data_ptr() + r0 * k * esz, k, dw.data_ptr(), rows, k, n, None, dtype,
+                      ws.data_ptr(), ws_bytes, st, tag="linear")
+                grads += [dw, g.sum(0, dtype=torch.float32)]
+        return dx, None, grads[0], grads[1], grads[2], grads[3], None, None
+
+
+def split_rows_linear(x, n0: int, w0, b0, w1, b1, out_bf16: bool = False, precision: Optional[str] = None):
+    """(x[:n0] @ w0.T + b0, x[n0:] @ w1.T + b1) on the tcgen05 GEMM (x 2-D CUDA, widths multiples of 64)."""
+    dtype = _PRECISIONS[precision or _default_precision]
+    return SplitRowsLinearFn.apply(x, int(n0), w0, b0, w1, b1, dtype, out_bf16)
 
 
 class TableGatherFn(torch.autograd.Function):

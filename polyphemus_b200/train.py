@@ -50,7 +50,23 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     # training.py:307 overwrites the structure logits with the structure tensor itself
     s_as_logits = s_tensor.reshape(-1, *s_logits.shape[2:]).float()
     s_loss = F.binary_cross_entropy_with_logits(s_as_logits.reshape(-1), s_tensor.reshape(-1).float())
-    if lazy:
+    if lazy and c_logits.split is not None:
+        # rows sorted drum-first, each block = [own pitch head | duration head]: the targets follow the same permutation
+        out_d, out_o, perm, (wp, wu) = c_logits.split
+        t = out_d.size(1)
+        pitch_t = pitch_true.int().view(-1, t).index_select(0, perm)
+        dur_t = dur_true.int().view(-1, t).index_select(0, perm)
+        n_d = out_d.size(0)
+        pitch_sum, dur_sum = 0.0, 0.0
+        for out, sl in ((out_d, slice(0, n_d)), (out_o, slice(n_d, None))):
+            if out.size(0) == 0:
+                continue
+            nll_p, nll_u = ops.token_nll_segments(out.reshape(-1, out.size(-1)),
+                                                  [(0, wp, pitch_t[sl].reshape(-1), PITCH_PAD), (wp, wu, dur_t[sl].reshape(-1), DUR_PAD)])
+            pitch_sum, dur_sum = pitch_sum + nll_p.sum(), dur_sum + nll_u.sum()
+        pitch_loss = pitch_sum / (pitch_t != PITCH_PAD).sum()
+        dur_loss = dur_sum / (dur_t != DUR_PAD).sum()
+    elif lazy:
         # fused row-wise cross entropy on the three head outputs (pb_ce_fwd/bwd): the node's own pitch head is picked
         # by giving each head the targets with the other head's rows set to the ignored PAD id
         t = c_logits.drums.size(1)

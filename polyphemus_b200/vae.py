@@ -420,6 +420,17 @@ class ContentDecoder(nn.Module):
             s.x = ops.bar_expand(z_bar, bar_ptr, s.num_nodes)       # every node starts from its bar's code
         else:
             s.x = z_bar.index_select(0, s.distinct_bars).float()
+        bf16 = ops.get_precision() == "bf16"
+        dropout_active = self.training and self.dropout_layer.p > 0
+        fold = z_bar.is_cuda and not self.materialize_logits and not dropout_active and d % 64 == 0
+        if fold and getattr(s, "n_drum", None) is not None and ops.split_heads_enabled():
+            # loss-only consumers: rows leave the GCN drum nodes first, so that each block only gets the pitch head of
+            # its own instrument class (5/8 of the un-embedding GEMM and of the logits)
+            perm, n_drum = _drum_split(s)
+            h = self.graph_decoder(s, out_perm=perm, out_dtype=torch.bfloat16 if bf16 else torch.float32)
+            t = MAX_SIMU_TOKENS - 1
+            return self._folded_heads_split(h, self.chord_decoder.weight.view(t, 2, half, d),
+                                            self.chord_decoder.bias.view(t, 2, half), s.is_drum, perm, n_drum, bf16)
         h = self.graph_decoder(s)
         # chord_decoder emits, per token slot, a pitch half and a duration half (model.py:549-567). Applying the
         # two row-subsets of its weight separately gives the same numbers without slicing a [N, 15, d] activation
@@ -427,9 +438,7 @@ class ContentDecoder(nn.Module):
         t = MAX_SIMU_TOKENS - 1
         w = self.chord_decoder.weight.view(t, 2, half, d)
         b = self.chord_decoder.bias.view(t, 2, half)
-        bf16 = ops.get_precision() == "bf16"
-        dropout_active = self.training and self.dropout_layer.p > 0
-        if h.is_cuda and not self.materialize_logits and not dropout_active and d % 64 == 0:
+        if fold:
             return self._folded_heads(h, w, b, s.is_drum, bf16)
         h_pitch = ops.tc_linear(h, w[:, 0].reshape(t * half, d), b[:, 0].reshape(-1), out_bf16=bf16)
         h_dur = ops.tc_linear(h, w[:, 1].reshape(t * half, d), b[:, 1].reshape(-1), out_bf16=bf16)
@@ -488,6 +497,34 @@ class ContentDecoder(nn.Module):
         return parts
 
 
+    def _composed_heads(self, w, b):
+        """Per head (drum pitch, non-drum pitch, duration): W_head W_cd[t, half] [t, C64, d] and its bias [t, C64],
+        C padded to a multiple of 64 with zero rows / -inf bias."""
+        out = []
+        for lin, which in ((self.drums_pitch_emb, 0), (self.non_drums_pitch_emb, 0), (self.dur_emb, 1)):
+            hw, hb = lin.weight.float(), lin.bias.float()
+            pad = (-hw.size(0)) % 64
+            wc = torch.einsum("ch,thd->tcd", hw, w[:, which].float())
+            bc = torch.einsum("ch,th->tc", hw, b[:, which].float()) + hb
+            out.append((F.pad(wc, (0, 0, 0, pad)), F.pad(bc, (0, pad), value=float("-inf"))))
+        return out
+
+    def _folded_heads_split(self, h, w, b, is_drum, perm, n_drum: int, bf16: bool) -> "LogitParts":
+        """_folded_heads on rows sorted drum-first (``h`` = node features in ``perm`` order): the drum block goes through
+        [drum-pitch 192 | duration 128], the other block through [non-drum-pitch 192 | duration 128] — the pitch head a
+        node does not use (model.py:571-574 selects by is_drum) is never computed."""
+        t = w.size(0)
+        with torch.autocast(device_type=h.device.type, enabled=False):
+            (wd, bd), (wo, bo), (wu, bu) = self._composed_heads(w, b)
+            cols = wd.size(1) + wu.size(1)
+            w_d, b_d = torch.cat((wd, wu), dim=1).view(t * cols, -1), torch.cat((bd, bu), dim=1).view(-1)
+            w_o, b_o = torch.cat((wo, wu), dim=1).view(t * cols, -1), torch.cat((bo, bu), dim=1).view(-1)
+            out_d, out_o = ops.split_rows_linear(h, n_drum, w_d, b_d, w_o, b_o, out_bf16=bf16)
+        parts = LogitParts(None, None, None, is_drum)
+        parts.split = (out_d.view(-1, t, cols), out_o.view(-1, t, cols), perm, (wd.size(1), wu.size(1)))
+        return parts
+
+
 class LogitParts:
     """Content logits kept as the three head outputs (drum-pitch, non-drum-pitch, duration; width padded with -inf)
     plus the per-node drum flag — what ``c_logits`` is assembled from. ``dense()`` builds the reference's
@@ -496,8 +533,16 @@ class LogitParts:
     def __init__(self, drums, others, dur, is_drum):
         self.drums, self.others, self.dur, self.is_drum = drums, others, dur, is_drum
         self.combined, self.widths = None, None     # set when the three heads are column blocks of one matrix
+        # (drum rows [n_drum, t, wp + wu], other rows [.., t, wp + wu], perm, (wp, wu)): rows sorted drum-first, each
+        # block holding its own pitch head and the duration head
+        self.split = None
 
     def dense(self) -> torch.Tensor:
+        if self.split is not None:
+            out_d, out_o, perm, (wp, _) = self.split
+            rows = torch.cat((out_d, out_o), dim=0).float()
+            rows = torch.cat((rows[..., :N_PITCH_TOKENS], rows[..., wp:wp + N_DUR_TOKENS]), dim=-1)
+            return torch.empty_like(rows).index_copy_(0, perm, rows)
         pitch = torch.where(self.is_drum.view(-1, 1, 1), self.drums, self.others)
         return torch.cat((pitch[..., :N_PITCH_TOKENS], self.dur[..., :N_DUR_TOKENS]), dim=-1).float()
 
