@@ -735,7 +735,10 @@ class ChordEmbedFn(torch.autograd.Function):
                   _ffi.ptr(gcat_lo), 2 * d, d_t.data_ptr(), n, 2 * d, kk, None, dtype, ws.data_ptr(), ws_bytes, st,
                   tag="linear")
         d_tables = d_t.view(n_slots, vp, 2, d)[:, :vocab].permute(2, 0, 1, 3)
-        d_bias = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=dev)).sum(0)
+        if bf16:     # the prepared operand already holds the ReLU-masked gradient, one half per table set
+            d_bias = gcat_hi.view(n, 2, d).sum(0, dtype=torch.float32).sum(0)
+        else:
+            d_bias = torch.where(out > 0, g, torch.zeros((), dtype=g.dtype, device=dev)).sum(0)
         return d_tables, d_bias, None, None, None, None, None
 
 

@@ -40,7 +40,10 @@ def vae_losses(s_tensor, s_logits, c_tensor, c_logits, mu, log_var, beta: float 
     else:
         logits = c_logits.reshape(-1, c_logits.size(-1)).float()
         pitch_logits, dur_logits = logits[:, :N_PITCH_TOKENS], logits[:, N_PITCH_TOKENS:]
-    if c_tokens is not None:
+    if c_tokens is not None and lazy:
+        tgt = c_tokens[:, 1:, :].int()                       # [N, 15, 2]: the fused NLL takes int32 targets
+        pitch_true, dur_true = tgt[..., 0].reshape(-1), tgt[..., 1].reshape(-1)
+    elif c_tokens is not None:
         tgt = c_tokens[:, 1:, :].reshape(-1, 2).long()
         pitch_true, dur_true = tgt[:, 0], tgt[:, 1]
     else:
