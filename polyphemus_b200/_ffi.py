@@ -214,7 +214,29 @@ def ptr(t) -> int | None:
 
 
 def stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of the current stream of the current device (the callers sit inside ``on_device``). The private
+    accessor costs ~0.3 us against ~15 us for torch.cuda.current_stream(): at ~300 library calls per training step
+    that is a millisecond of host time per step."""
+    return torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice())
+
+
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def on_device(dev):
+    """``with on_device(t.device):`` — torch.cuda.device(dev) only when `dev` is not already current (entering and
+    leaving the real guard costs ~10 us, and every op of the path used to do it)."""
+    if dev.index is None or dev.index == torch._C._cuda_getDevice():
+        return _NO_GUARD
+    return torch.cuda.device(dev)
 
 
 def require_cuda(*tensors) -> None:

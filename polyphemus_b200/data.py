@@ -42,7 +42,7 @@ def decode_samples(c_disk: torch.Tensor, s_disk: torch.Tensor, n_bars: int, devi
         device = c_disk.device if c_disk.is_cuda else torch.device("cuda", torch.cuda.current_device())
     c_dev = c_disk.to(device, non_blocking=True).contiguous()
     s_dev = s_disk.to(device, non_blocking=True).contiguous()
-    with torch.cuda.device(device):
+    with _ffi.on_device(device):
         st = _ffi.stream()
         s_tensor = torch.empty((bsz, n_bars, N_TRACKS, N_TIMESTEPS), dtype=torch.bool, device=device)
         _ffi.call("pb_dataset_structure", s_dev.view(torch.uint8).data_ptr(), bsz, n_bars, s_tensor.data_ptr(), st)
@@ -75,7 +75,7 @@ def mtp_from_logits(c_logits: torch.Tensor, s_tensor: torch.Tensor) -> torch.Ten
     c_logits = c_logits.contiguous()
     mtp = torch.empty(tuple(s_tensor.shape) + (n_tok, d_tok), dtype=c_logits.dtype, device=dev)
     s_u8 = active.to(torch.uint8)
-    with torch.cuda.device(dev):
+    with _ffi.on_device(dev):
         _ffi.call("pb_mtp_from_logits", c_logits.data_ptr(), n_tok * d_tok, _ffi.PB_BF16 if c_logits.dtype == torch.bfloat16 else _ffi.PB_F32,
                   s_u8.data_ptr(), node_of_cell.data_ptr(), n_cells, n_tok, d_tok, PITCH_EOS, PITCH_PAD, mtp.data_ptr(),
                   _ffi.stream())

@@ -48,7 +48,7 @@ class CsrPlan:
         self.dist_item_ptr = torch.empty(_ffi.N_DISTS + 1, dtype=torch.int32, device=dev)
         ws_bytes = lib.pb_csr_workspace_bytes(n, e, r)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _ffi.call("pb_csr_build", edge_index.data_ptr(), edge_type.data_ptr(), edge_dist.data_ptr(), n, e, r,
                       self.in_ptr.data_ptr(), self.in_edge.data_ptr(), self.in_eid.data_ptr(),
                       self.out_ptr.data_ptr(), self.out_rec.data_ptr(), self.dist_perm.data_ptr(),
@@ -67,7 +67,7 @@ class CsrPlan:
         backward's flat record stream in visiting order (pb_csr_bwd_stream)."""
         st = self.struct
         st.visit_meta = st.bwd_stream = st.visit_edge_ptr = None
-        with torch.cuda.device(self.device):
+        with _ffi.on_device(self.device):
             _ffi.call("pb_csr_visit_meta", ctypes.byref(st), self.visit_meta.data_ptr(), _ffi.stream())
             st.visit_meta = self.visit_meta.data_ptr()
             self.visit_edge_ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int32, device=self.device)
@@ -144,7 +144,7 @@ class Graph:
         if self._edge_attrs is None:
             e = self.edge_type.numel()
             out = torch.empty((e, N_TIMESTEPS + 1), dtype=torch.float32, device=self.edge_type.device)
-            with torch.cuda.device(out.device):
+            with _ffi.on_device(out.device):
                 _ffi.call("pb_edge_attrs_encode", self.edge_type.data_ptr(), self.edge_dist.data_ptr(), e,
                           out.data_ptr(), _ffi.stream())
             self._edge_attrs = out
@@ -225,7 +225,7 @@ def graphs_from_tensor(s_tensor: torch.Tensor, device: Optional[torch.device] = 
     dev = s_u8.device
     lib = _ffi.lib()
     total_bars = bsz * n_bars
-    with torch.cuda.device(dev):
+    with _ffi.on_device(dev):
         st = _ffi.stream()
         bar_bits = torch.empty((total_bars, 4), dtype=torch.int32, device=dev)
         node_ptr = torch.empty(total_bars + 1, dtype=torch.int32, device=dev)
@@ -306,7 +306,7 @@ def decode_edge_attrs(edge_type: torch.Tensor, edge_attr: torch.Tensor):
     t_out = torch.empty(e, dtype=torch.uint8, device=dev)
     d_out = torch.empty(e, dtype=torch.uint8, device=dev)
     if e:
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _ffi.call("pb_edge_attrs_decode", edge_type.data_ptr(), edge_type.stride(0), edge_attr.data_ptr(),
                       edge_attr.stride(0), e, t_out.data_ptr(), d_out.data_ptr(), _ffi.stream())
     return t_out, d_out

@@ -169,7 +169,7 @@ def prefetch_keep_bits(plan: CsrPlan, d: int, p: float, n_calls: int):
     bufs = [torch.empty(nbytes // 2, dtype=torch.int16, device=dev) for _ in range(n_calls)]   # owned by `main`
     side.wait_stream(main)               # the buffers' previous users on `main` are done before the side stream writes
     out = []
-    with torch.cuda.device(dev):
+    with _ffi.on_device(dev):
         for seed, bits in zip(seeds, bufs):
             _call("pb_dropout_bits", plan.n_edges, d, float(p), int(seed), bits.data_ptr(), side.cuda_stream)
             ev = torch.cuda.Event()
@@ -206,7 +206,7 @@ class RGCLayerFn(torch.autograd.Function):
         weight, root = weight.contiguous(), root.contiguous()
         nn_w, nn_b = nn_w.contiguous(), nn_b.contiguous()
         bias_c = None if bias is None else bias.contiguous()
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             st = _ffi.stream()
             table = _edge_table(nn_w, nn_b, d, st)
             a_hi, a_lo = _operand(n, k, cfg.dtype, dev)
@@ -283,7 +283,7 @@ class RGCLayerFn(torch.autograd.Function):
         lib = _ffi.lib()
         struct = ctx.struct
         groups = None if struct is None else struct.groups_ref()
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             st = _ffi.stream()
             # padding rows of the structured layout must be zero: pb_bn_relu_res_bwd writes them itself
             g_hi, g_lo = _operand(n, d, cfg.dtype, dev, zero=struct is not None and not cfg.batch_norm)
@@ -399,7 +399,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
         out_bf16 = bool(out_bf16 and dtype == _ffi.PB_BF16)
         out = torch.empty((m, n), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=dev)
         bias_f = None if bias is None else bias.float().contiguous()
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _call("pb_gemm_nt", x_hi.data_ptr(), _ffi.ptr(x_lo), k, w_hi.data_ptr(), _ffi.ptr(w_lo), k,
                   _ffi.ptr(bias_f), out.data_ptr(), n, m, n, k, dtype, int(out_bf16), _ffi.stream(), tag="linear")
         ctx.save_for_backward(x_hi, x_lo, weight)
@@ -415,7 +415,7 @@ class TensorCoreLinearFn(torch.autograd.Function):
         dev = g.device
         g_hi, g_lo = _as_operand(g, dtype)
         lib = _ffi.lib()
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             st = _ffi.stream()
             dx = None
             if ctx.needs_input_grad[0]:
@@ -451,7 +451,7 @@ class SplitRowsLinearFn(torch.autograd.Function):
         odt = torch.bfloat16 if out_bf16 else torch.float32
         esz = x_hi.element_size()
         outs, saved_w = [], []
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             for r0, rows, w, b in ((0, n0, w0, b0), (n0, m - n0, w1, b1)):
                 n = w.shape[0]
                 out = torch.empty((rows, n), dtype=odt, device=dev)
@@ -477,7 +477,7 @@ class SplitRowsLinearFn(torch.autograd.Function):
         dx_bf16 = dtype == _ffi.PB_BF16 and ctx.x_dtype == torch.bfloat16
         dx = torch.empty((m, k), dtype=torch.bfloat16 if dx_bf16 else torch.float32, device=dev)
         grads = []
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             st = _ffi.stream()
             for r0, rows, w, g in ((0, n0, w0, g0), (n0, m - n0, w1, g1)):
                 n = w.shape[0]
@@ -534,7 +534,7 @@ class TableGatherFn(torch.autograd.Function):
         d_table = torch.empty((vp, c), dtype=torch.float32, device=dev)
         ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(m, c, vp, dtype)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             _call("pb_rgcn_gemm_bwd_weight", onehot.data_ptr(), _ffi.ptr(oh_lo), vp, g_hi.data_ptr(), _ffi.ptr(g_lo), c,
                   d_table.data_ptr(), m, c, vp, None, dtype, ws.data_ptr(), ws_bytes, _ffi.stream(), tag="linear")
         return d_table[:vocab].to(ctx.table_dtype), None, None
@@ -564,7 +564,7 @@ def _act_code(dtype: torch.dtype) -> int:
 
 def _rows_scatter(x, pos, struct, out_dtype):
     out = torch.empty((struct.n_padded, x.size(1)), dtype=out_dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _ffi.on_device(x.device):
         _call("pb_rows_scatter", x.data_ptr(), _act_code(x.dtype), pos.data_ptr(), x.size(0), x.size(1), out.data_ptr(),
               _act_code(out_dtype), struct.n_padded, struct.groups_ref(), _ffi.stream())
     return out
@@ -572,7 +572,7 @@ def _rows_scatter(x, pos, struct, out_dtype):
 
 def _rows_gather(xp, pos, out_dtype):
     out = torch.empty((pos.numel(), xp.size(1)), dtype=out_dtype, device=xp.device)
-    with torch.cuda.device(xp.device):
+    with _ffi.on_device(xp.device):
         _call("pb_rows_gather", xp.data_ptr(), _act_code(xp.dtype), pos.data_ptr(), pos.numel(), xp.size(1), out.data_ptr(),
               _act_code(out_dtype), _ffi.stream())
     return out
@@ -622,7 +622,7 @@ class BarPoolFn(torch.autograd.Function):
         h, gate = h.float().contiguous(), gate.float().contiguous().view(-1)
         alpha = torch.zeros(n, dtype=torch.float32, device=h.device)
         out = torch.empty((n_bars, d), dtype=torch.float32, device=h.device)
-        with torch.cuda.device(h.device):
+        with _ffi.on_device(h.device):
             _call("pb_bar_pool_fwd", h.data_ptr(), d, gate.data_ptr(), bar_ptr.data_ptr(), n_bars, d, alpha.data_ptr(),
                   out.data_ptr(), _ffi.stream())
         ctx.save_for_backward(h, alpha, bar_ptr)
@@ -636,7 +636,7 @@ class BarPoolFn(torch.autograd.Function):
         g_out = g_out.float().contiguous()
         g_h = torch.empty_like(h)
         g_gate = torch.empty(n, dtype=torch.float32, device=h.device)
-        with torch.cuda.device(h.device):
+        with _ffi.on_device(h.device):
             _call("pb_bar_pool_bwd", h.data_ptr(), d, alpha.data_ptr(), bar_ptr.data_ptr(), n_bars, d, g_out.data_ptr(),
                   g_h.data_ptr(), d, g_gate.data_ptr(), _ffi.stream())
         return g_h, g_gate, None
@@ -650,7 +650,7 @@ class BarExpandFn(torch.autograd.Function):
         n_bars, d = z.shape
         z = z.float().contiguous()
         x = torch.empty((n_nodes, d), dtype=torch.float32, device=z.device)
-        with torch.cuda.device(z.device):
+        with _ffi.on_device(z.device):
             _call("pb_bar_expand_fwd", z.data_ptr(), bar_ptr.data_ptr(), n_bars, d, x.data_ptr(), d, _ffi.stream())
         ctx.save_for_backward(bar_ptr)
         ctx.shape = (n_bars, d)
@@ -662,7 +662,7 @@ class BarExpandFn(torch.autograd.Function):
         n_bars, d = ctx.shape
         g_x = g_x.float().contiguous()
         g_z = torch.empty((n_bars, d), dtype=torch.float32, device=g_x.device)
-        with torch.cuda.device(g_x.device):
+        with _ffi.on_device(g_x.device):
             _call("pb_bar_expand_bwd", g_x.data_ptr(), d, bar_ptr.data_ptr(), n_bars, d, g_z.data_ptr(), _ffi.stream())
         return g_z, None, None
 
@@ -701,7 +701,7 @@ class ChordEmbedFn(torch.autograd.Function):
         tab = (tables.to(torch.bfloat16) if dtype == _ffi.PB_BF16 else tables.float()).contiguous()
         bias_f = bias.float().contiguous()
         out = torch.empty((n, d), dtype=torch.float32, device=tables.device)
-        with torch.cuda.device(tables.device):
+        with _ffi.on_device(tables.device):
             _call("pb_chord_embed_fwd", tokens.data_ptr(), tokens.stride(0), tok_offset, n_slots, set_id.data_ptr(),
                   tab.data_ptr(), dtype, vocab, dur_off, d, bias_f.data_ptr(), out.data_ptr(), d, n, _ffi.stream())
         ctx.save_for_backward(tokens, set_id, out)
@@ -726,7 +726,7 @@ class ChordEmbedFn(torch.autograd.Function):
         lib = _ffi.lib()
         ws_bytes = lib.pb_rgcn_gemm_bwd_weight_workspace_bytes_for(n, 2 * d, kk, dtype)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        with torch.cuda.device(dev):
+        with _ffi.on_device(dev):
             st = _ffi.stream()
             _call("pb_chord_embed_bwd_prep", tokens.data_ptr(), tokens.stride(0), tok_offset, n_slots, set_id.data_ptr(),
                   dur_off, vp, d, out.data_ptr(), d, g.data_ptr(), d, dtype, onehot.data_ptr(), gcat_hi.data_ptr(),
@@ -763,7 +763,7 @@ class TokenNllFn(torch.autograd.Function):
         dtype = _ffi.PB_BF16 if logits.dtype == torch.bfloat16 else _ffi.PB_F32
         nll = torch.empty(rows, dtype=torch.float32, device=logits.device)
         lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
-        with torch.cuda.device(logits.device):
+        with _ffi.on_device(logits.device):
             _call("pb_ce_fwd", logits.data_ptr(), logits.stride(0), dtype, rows, classes, target.data_ptr(),
                   int(ignore_index), nll.data_ptr(), lse.data_ptr(), _ffi.stream())
         ctx.save_for_backward(logits, target, lse)
@@ -776,7 +776,7 @@ class TokenNllFn(torch.autograd.Function):
         rows, classes = logits.shape
         g = g.float().contiguous()
         grad = torch.empty((rows, classes), dtype=logits.dtype, device=logits.device)
-        with torch.cuda.device(logits.device):
+        with _ffi.on_device(logits.device):
             _call("pb_ce_bwd", logits.data_ptr(), logits.stride(0), ctx.dtype, rows, classes, target.data_ptr(),
                   ctx.ignore_index, lse.data_ptr(), g.data_ptr(), grad.data_ptr(), classes, _ffi.stream())
         return grad, None, None
@@ -806,7 +806,7 @@ class TokenNllSegmentsFn(torch.autograd.Function):
         nll = torch.empty((n, rows), dtype=torch.float32, device=logits.device)
         lse = torch.empty((n, rows), dtype=torch.float32, device=logits.device)
         widths, ptrs, ignore = _segment_args(specs, targets)
-        with torch.cuda.device(logits.device):
+        with _ffi.on_device(logits.device):
             _call("pb_ce_rows_fwd", logits.data_ptr(), logits.stride(0), dtype, rows, n, widths, ptrs, ignore,
                   nll.data_ptr(), lse.data_ptr(), _ffi.stream())
         ctx.save_for_backward(logits, lse, *targets)
@@ -822,7 +822,7 @@ class TokenNllSegmentsFn(torch.autograd.Function):
                                 for g in gs]).contiguous()
         grad = torch.empty((rows, cols), dtype=logits.dtype, device=logits.device)
         widths, ptrs, ignore = _segment_args(ctx.specs, targets)
-        with torch.cuda.device(logits.device):
+        with _ffi.on_device(logits.device):
             _call("pb_ce_rows_bwd", logits.data_ptr(), logits.stride(0), ctx.dtype, rows, n, widths, ptrs, ignore,
                   lse.data_ptr(), row_grad.data_ptr(), grad.data_ptr(), cols, _ffi.stream())
         return (grad, None) + (None,) * n
@@ -858,6 +858,6 @@ def token_nll(logits: torch.Tensor, target: torch.Tensor, ignore_index: int) -> 
 def dropout_keep_mask(n_edges: int, d: int, p_drop: float, seed: int, device) -> torch.Tensor:
     """The keep-mask pb_agg_fwd/bwd use for (seed, p): bool [E, d], indexed by edge_index column."""
     keep = torch.empty((n_edges, d), dtype=torch.uint8, device=device)
-    with torch.cuda.device(device):
+    with _ffi.on_device(device):
         _call("pb_dropout_mask", n_edges, d, float(p_drop), int(seed), keep.data_ptr(), _ffi.stream())
     return keep.bool()

@@ -248,6 +248,12 @@ class GradAllReducer:
     never receive a gradient — the 12 ``decoder.s_decoder.*`` tensors, whose loss term is constant, training.py:307 —
     keep a zero slot, identically on every rank), waits, and points every ``.grad`` at its slice of the buffer for
     the optimizer. The buckets produced last are small (``tail_mb``) so that the exposed tail after backward is short.
+
+    A parameter that never gets a gradient would hold back its bucket — and, the launches being ordered, every bucket
+    behind it — until ``finish()``: the whole exchange would sit exposed after backward. The first ``finish()`` therefore
+    agrees across ranks (one MAX all-reduce of a flag vector) on the parameters NO rank produced a gradient for; from
+    then on they count as ready from the start of every step. Should one of them receive a gradient later it is
+    packed if its bucket has not gone out yet, counted normally from the next step on, and reported once.
     """
 
     def __init__(self, params, bucket_mb: float = 32.0, process_group=None, tail_mb: float = 4.0):
@@ -281,6 +287,10 @@ class GradAllReducer:
                 start, members = off, []
         if members:
             self.buckets.append((start, off, members))
+        self._absent = set()                       # parameters without a gradient on every rank (agreed at the first step)
+        self._absent_count = [0] * len(self.buckets)
+        self._calibrated = False
+        self._seen = set()
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._next = 0
@@ -324,8 +334,27 @@ class GradAllReducer:
     def _hook(self, p) -> None:
         if not self.sync:
             return
+        if not self._calibrated:
+            self._seen.add(p)
+        if p in self._absent:                       # counted as ready already; count it normally from the next step on
+            self._absent.discard(p)
+            self._absent_count[self._bucket_of[p]] -= 1
+            import warnings
+            warnings.warn("GradAllReducer: a parameter without gradient in the first step received one later; if its "
+                          "bucket had already been reduced this step's contribution of it is dropped on this rank")
+            return
         self._ready[self._bucket_of[p]] += 1
         self._advance()
+
+    def _calibrate(self) -> None:
+        """Agree on the parameters nobody produced a gradient for (first step only: one small all-reduce, one read-back)."""
+        flags = torch.tensor([1.0 if p in self._seen else 0.0 for p in self.params], device=self.flat.device)
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=self.group)
+        for p, f in zip(self.params, flags.tolist()):
+            if f == 0.0:
+                self._absent.add(p)
+                self._absent_count[self._bucket_of[p]] += 1
+        self._calibrated, self._seen = True, set()
 
     def zero_grad(self) -> None:
         for p in self.params:
@@ -333,17 +362,21 @@ class GradAllReducer:
         if self.flat is None:
             return
         self.flat.zero_()
-        self._ready = [0] * len(self.buckets)
+        self._ready = list(self._absent_count)
         self._launched = [False] * len(self.buckets)
         self._next = 0
+        self.launched_in_backward = 0
 
     def finish(self) -> None:
         """Flush incomplete buckets in order, wait for all reductions, expose the buffer slices as ``.grad``."""
         if self.flat is None:
             return
+        self.launched_in_backward = self._next       # buckets that went out while backward was still running
         for b in range(len(self.buckets)):
             self._launch(b)
         self._next = len(self.buckets)
+        if self.sync and not self._calibrated:
+            self._calibrate()
         for h in self._handles:
             h.wait()
         self._handles = []

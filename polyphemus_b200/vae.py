@@ -280,7 +280,7 @@ class ContentEncoder(nn.Module):
                 # full device sync in the middle of the forward pass)
                 both = torch.empty((2, N_PITCH_TOKENS + N_DUR_TOKENS), dtype=torch.int64, device=tokens.device)
                 flags = is_drum.view(torch.uint8) if is_drum.dtype == torch.bool else is_drum
-                with torch.cuda.device(tokens.device):
+                with _ffi.on_device(tokens.device):
                     _ffi.call("pb_token_hist", tokens.data_ptr(), tokens.stride(0), 2, t, flags.data_ptr(), tokens.size(0),
                               N_PITCH_TOKENS, N_DUR_TOKENS, both.data_ptr(), _ffi.stream())
                 cnt_p, cnt_d = both[:, :N_PITCH_TOKENS], both[:, N_PITCH_TOKENS:]

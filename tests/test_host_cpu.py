@@ -174,12 +174,16 @@ unused = model[3]                      # never used in forward: grad stays None 
 red = GradAllReducer(model.parameters(), bucket_mb=0.0001)
 data = torch.randn(world * 6, 8, generator=torch.Generator().manual_seed(1))
 target = torch.randn(world * 6, 4, generator=torch.Generator().manual_seed(2))
-for step in range(2):
+for step in range(3):
     red.zero_grad()
     shard = slice(rank * 6, (rank + 1) * 6)
     loss = ((model[2](model[1](model[0](data[shard]))) - target[shard]) ** 2).mean()
     loss.backward()
     red.finish()
+    # the unused layer is registered last = first buckets: before the first finish() has agreed on the gradient-less
+    # parameters nothing can go out during backward, afterwards every bucket does
+    assert red.launched_in_backward == (0 if step == 0 else len(red.buckets)), (step, red.launched_in_backward)
+assert len(red._absent) == 2
 # single-process reference: average of per-shard gradients
 ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.ReLU(), torch.nn.Linear(16, 4), torch.nn.Linear(4, 4))
 ref.load_state_dict(model.state_dict())

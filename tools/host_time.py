@@ -32,7 +32,8 @@ import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
 for i in range(4): step(graphs[i])
 pr.disable(); torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(35)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
+pstats.Stats(pr).sort_stats("tottime").print_stats(45)
 print("---- sync debug: every host sync inside one step")
 torch.cuda.set_sync_debug_mode("warn")
 import warnings
@@ -43,3 +44,21 @@ with warnings.catch_warnings(record=True) as w:
 torch.cuda.set_sync_debug_mode("default")
 for x in w:
     print("SYNC:", str(x.message)[:100], "@", x.filename.split("/")[-1], x.lineno)
+print("---- host time per ABI entry point (perf_counter around the ctypes call), 4 steps")
+import collections
+from polyphemus_b200 import _ffi as F
+acc = collections.defaultdict(lambda: [0, 0.0])
+orig = F.call
+def timed_call(name, *a, tag=None):
+    t = time.perf_counter()
+    orig(name, *a, tag=tag)
+    e = acc[name]; e[0] += 1; e[1] += time.perf_counter() - t
+F.call = timed_call
+torch.cuda.synchronize()
+for i in range(4):
+    step(device_batch(host, dev)); torch.cuda.synchronize()   # synchronised: no launch-queue back-pressure in the numbers
+F.call = orig
+tot = sum(v[1] for v in acc.values())
+print(f"total {1e3*tot/4:.2f} ms/step in {sum(v[0] for v in acc.values())//4} calls/step")
+for k, v in sorted(acc.items(), key=lambda kv: -kv[1][1])[:25]:
+    print(f"{k:40s} {v[0]//4:4d} calls/step  {1e6*v[1]/v[0]:7.1f} us/call  {1e3*v[1]/4:6.2f} ms/step")
