@@ -1,3 +1,12 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 120 > gpurun_out/t_k.log 2>&1; tail -3 gpurun_out/t_k.log
-for r in 0 1; do echo "PIPE=$r"; PB200_AGG_FWD_PIPE=$r timeout 120 python tools/bench_agg.py --which fwd --iters 30 2>&1 | tail -1; done
+for i in 1 2; do
+timeout 600 python bench.py --steps 20 --warmup 5 --no-secondary > gpurun_out/b_cur.log 2>&1
+python - <<PY
+import json
+for l in open('gpurun_out/b_cur.log'):
+    if l.startswith('{'):
+        j=json.loads(l); print('cur', j['ms_per_step'], j['e2e']['ms_per_step'], j['clocks']['sm_mhz'], 'ours', j['our_kernels_ms_per_step'])
+        for k in j['kernels']:
+            if 'agg' in k['kernel']: print('   ', k['kernel'], round(k['avg_ms'],3), k.get('frac') and round(k['frac'],3))
+PY
+done

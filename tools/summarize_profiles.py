@@ -83,9 +83,9 @@ def traffic_json():
     import re
 
     families = {   # ABI call -> (summary file, kernel-name prefixes whose launches make up one call)
-        "pb_agg_fwd": ("aggfwd", ["agg_fwd_kernel"]),
+        "pb_agg_fwd": ("aggfwd", ["agg_fwd_pipe_kernel", "agg_fwd_kernel"]),
         "pb_agg_bwd": ("aggbwd", ["agg_bwd_dx_kernel"]),
-        "pb_agg_bwd_fused": ("aggbwdtc", ["agg_bwd_tc_kernel"]),
+        "pb_agg_bwd_fused": ("aggbwdring", ["agg_bwd_ring_kernel"]),
         "pb_dist_reduce": ("distred", ["dist_reduce_kernel"]),
         "pb_rgcn_gemm_fwd": ("gemm", ["gemm_tcgen05_kernel"]),
         "pb::gemm_tcgen05_kernel": ("gemm", ["gemm_tcgen05_kernel"]),     # mean of the captured launches (fwd, bwd_weight, bwd_data)
