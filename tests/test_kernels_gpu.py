@@ -653,7 +653,10 @@ def test_chord_embed_matches_dense_formulation(cuda, precision, d):
     scale = float(tab.grad.abs().max())
     tol = dict(rtol=1e-4, atol=1e-5 * scale) if precision == "fp32" else dict(rtol=2e-2, atol=2e-2 * scale)
     torch.testing.assert_close(t_dev.grad.cpu().double(), tab.grad, **tol)
-    torch.testing.assert_close(b_dev.grad.cpu().double(), bias64.grad, rtol=1e-4, atol=1e-4 * float(bias64.grad.abs().max()))
+    # fp32 mode: exact fp32 column sums. bf16 mode: the bias gradient is summed from the same bf16-rounded, ReLU-masked
+    # operand the table-gradient GEMM contracts (2^-9 relative rounding per term, fp32 accumulation)
+    b_tol = 1e-4 if precision == "fp32" else 5e-3
+    torch.testing.assert_close(b_dev.grad.cpu().double(), bias64.grad, rtol=b_tol, atol=b_tol * float(bias64.grad.abs().max()))
 
 
 def _random_bar_ptr(n_bars, gen, max_nodes=128):
