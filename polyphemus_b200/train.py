@@ -16,6 +16,8 @@ from dataclasses import dataclass
 from typing import Optional
 
 import numpy as np
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -410,6 +412,7 @@ class TrainStep:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.98), eps: float = 1e-9, autocast_bf16: bool = False,
                  beta_kld: float = 0.0, bucket_mb: float = 32.0):
         self.model = model
+        bucket_mb = float(os.environ.get("PB200_BUCKET_MB", bucket_mb))
         self.reducer = GradAllReducer(model.parameters(), bucket_mb=bucket_mb)
         self.opt = torch.optim.Adam(model.parameters(), lr=lr, betas=betas, eps=eps, fused=model_is_cuda(model))
         self.autocast_bf16 = autocast_bf16
