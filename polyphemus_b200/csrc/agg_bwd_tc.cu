@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
   uint64_t* done = bars + 2 * kTcStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   volatile int* progress = reinterpret_cast<volatile int*>(tmem_slot + 1);   // sources finished by the gather warps
+  // stages whose MMAs have been issued. A gather warp may be more than a lap of the stage ring ahead of the tensor core
+  // (skewed out-degrees: one warp works through a 400-edge hub while the others are done with everything behind it), and the
+  // parity of `empty` alone cannot tell "the previous use is done" from "two uses ago is done": the warp first waits until
+  // the previous use of its stage has at least been issued, then the parity wait is unambiguous.
+  volatile int* mma_front = reinterpret_cast<volatile int*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
@@ -117,6 +122,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
     for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, kTcStageEdges); mbar_init(empty + s, 1); }
     mbar_init(done, 1);
     *progress = 0;
+    *mma_front = 0;
     fence_barrier_init();
   }
   if (warp == kTcProducers) tmem_alloc(tmem_slot, kMB * kTcN < 32 ? 32 : kMB * kTcN);
@@ -165,6 +171,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
           }
         }
         umma_commit(empty + st);        // the stage may be refilled once these MMAs have read it
+        *mma_front = g + 1;
       }
       if (n_total > 0) umma_commit(done);
     }
@@ -285,7 +292,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
         const int p = pos0 + i;
         const int sidx = p / kTcStageEdges, st = sidx & (kTcStages - 1), slot = p & (kTcStageEdges - 1);
         if (sidx != stage_ok) {                                    // warp-uniform: first slot this warp writes in the stage
-          mbar_wait_backoff(empty + st, (uint32_t)(((sidx / kTcStages) & 1) ^ 1));
+          while (*mma_front <= sidx - kTcStages) __nanosleep(PB_TC_SLEEP);    // its previous use has been issued ...
+          mbar_wait_backoff(empty + st, (uint32_t)(((sidx / kTcStages) & 1) ^ 1));   // ... and has been read
           stage_ok = sidx;
         }
         const uint32_t swz = (uint32_t)(slot & 7) << 4;
@@ -466,6 +474,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
   uint64_t* empty = bars + kTcStages;          // [kTcStages]: tcgen05.commit -> the stage may be refilled
   uint64_t* done = bars + 2 * kTcStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  volatile int* mma_front = reinterpret_cast<volatile int*>(tmem_slot + 1);   // stages whose MMAs have been issued (see above)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t per = (n_nodes + gridDim.x - 1) / gridDim.x;
@@ -481,6 +490,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
   if (warp == kRgWarps && lane == 0) {
     for (int s = 0; s < kTcStages; ++s) { mbar_init(full + s, kTcStageEdges); mbar_init(empty + s, 1); }
     mbar_init(done, 1);
+    *mma_front = 0;
     fence_barrier_init();
   }
   if (warp == kRgWarps) tmem_alloc(tmem_slot, kMB * kTcN < 32 ? 32 : kMB * kTcN);
@@ -534,6 +544,7 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
           }
         }
         umma_commit(empty + st);
+        *mma_front = g + 1;
       }
       if (n_total > 0) umma_commit(done);
     }
@@ -582,8 +593,13 @@ __global__ void __launch_bounds__(kRgThreads, 1) agg_bwd_ring_kernel(
         for (int sx = max(pbase / kTcStageEdges, load_ok + 1); sx <= s_last; ++sx) {
           uint64_t* bar = empty + (sx & (kTcStages - 1));
           const uint32_t par = (uint32_t)(((sx / kTcStages) & 1) ^ 1);
-          if (blocking) mbar_wait_backoff(bar, par);
-          else if (!mbar_test(bar, par)) return false;
+          // the stage's previous use must have been issued before the parity of `empty` means "it has been read"
+          if (blocking) {
+            while (*mma_front <= sx - kTcStages) __nanosleep(PB_TC_SLEEP);
+            mbar_wait_backoff(bar, par);
+          } else if (*mma_front <= sx - kTcStages || !mbar_test(bar, par)) {
+            return false;
+          }
           load_ok = sx;
         }
         for (int i = 0; i < n; ++i) {

@@ -398,6 +398,113 @@ def test_agg_bwd_fused_foreign_graph_high_degree(cuda):
     torch.testing.assert_close(g_w.double().cpu(), table.grad.t(), rtol=1e-5, atol=1e-5 * scale)
 
 
+@pytest.mark.parametrize("act", ["bf16", "fp32"])
+@pytest.mark.parametrize("d", [256, 512])
+def test_agg_bwd_tensor_core_foreign_graph_high_degree(cuda, act, d):
+    """Both tensor-core backward kernels (bf16 rows: cp.async ring kernel; fp32 rows: register-gather kernel) on an
+    arbitrary edge list with the generic 6-relation plan: a hub with 400 out-edges (more than the 128 ring slots: the
+    synchronous 32-edge chunks wrap the stages inside ONE source), 50 parallel self-loops, isolated nodes, dropout on.
+    gx bit-identical to the legacy two-kernel path, table gradient equal up to fp32 summation order."""
+    from polyphemus_b200.graph import CsrPlan
+
+    ffi = _ffi()
+    lib = ffi.lib()
+    n, e = 300, 6400
+    gen = torch.Generator().manual_seed(11 + d)
+    ei = torch.randint(0, n - 10, (2, e), generator=gen)            # the last 10 nodes are isolated
+    ei[:, :50] = 3                                                  # 50 parallel self-loops on node 3
+    ei[0, 50:450] = 5                                               # hub: 400 out-edges of node 5
+    et = torch.randint(0, 6, (e,), generator=gen, dtype=torch.uint8)
+    ed = torch.randint(0, 32, (e,), generator=gen, dtype=torch.uint8)
+    plan = CsrPlan(ei.to(cuda), et.to(cuda), ed.to(cuda), n)
+    k = 7 * d
+    adt = torch.bfloat16 if act == "bf16" else torch.float32
+    acode = ffi.PB_BF16 if act == "bf16" else ffi.PB_F32
+    x = torch.randn(n, d, generator=gen).to(cuda).to(adt)
+    gy = torch.randn(n, d, generator=gen).to(cuda).to(adt)
+    d_a = torch.randn(n, k, generator=gen).to(cuda).to(torch.bfloat16)
+    table = (torch.randn(32, d, generator=gen) * 0.5).to(cuda)
+    p_drop = 0.1
+    bits = keep_bits(e, d, p_drop, 4242, cuda)
+    gx0 = torch.empty(n, d, dtype=adt, device=cuda)
+    q_buf = torch.empty(e, d, dtype=torch.bfloat16, device=cuda)
+    parts0 = torch.empty(plan.n_dist_items, d, device=cuda)
+    ffi.check(lib.pb_agg_bwd(plan.ref(), ptr(x), d, ptr(table), ptr(d_a), k, ffi.PB_BF16, ptr(gy), ptr(gx0), ptr(q_buf), ptr(parts0),
+                             ptr(bits), p_drop, acode, st()), "agg_bwd")
+    gw0, gb0 = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+    ffi.check(lib.pb_edge_table_bwd(ptr(parts0), ptr(plan.dist_item_ptr), d, ptr(gw0), ptr(gb0), st()), "table_bwd")
+    n_part = lib.pb_agg_bwd_num_partials(n, d, ffi.PB_BF16)
+    outs = []
+    for _ in range(2):
+        gx1 = torch.full((n, d), float("nan"), dtype=adt, device=cuda)
+        parts1 = torch.full((n_part, 32, d), float("nan"), device=cuda)
+        ffi.check(lib.pb_agg_bwd_fused(plan.ref(), ptr(x), d, ptr(table), ptr(d_a), k, ffi.PB_BF16, ptr(gy), ptr(gx1), ptr(parts1),
+                                       ptr(bits), p_drop, acode, st()), "agg_bwd_fused")
+        gw1, gb1 = torch.empty(d, 32, device=cuda), torch.empty(d, device=cuda)
+        ffi.check(lib.pb_edge_table_bwd_fused(ptr(parts1), n_part, d, ptr(gw1), ptr(gb1), st()), "table_bwd_fused")
+        outs.append((gx1, parts1, gw1))
+    (gx1, parts1, gw1), (gx2, parts2, gw2) = outs
+    assert torch.equal(gx1, gx0)
+    assert torch.equal(gx1, gx2) and torch.equal(parts1, parts2) and torch.equal(gw1, gw2)
+    scale = float(gw0.abs().max())
+    torch.testing.assert_close(gw1, gw0, rtol=1e-4, atol=2e-5 * scale)
+
+
+def test_split_rows_linear_matches_two_linears(cuda):
+    """ops.split_rows_linear (the content decoder's un-embedding by instrument class): values and all gradients equal two
+    F.linear calls on the row blocks, including an empty first / second block."""
+    from polyphemus_b200 import ops
+
+    gen = torch.Generator().manual_seed(3)
+    m, k, n = 300, 128, 192
+    for n0 in (0, 77, 300):
+        x = torch.randn(m, k, generator=gen).to(cuda).requires_grad_(True)
+        w0, w1 = (torch.randn(n, k, generator=gen).to(cuda).requires_grad_(True) for _ in range(2))
+        b0, b1 = (torch.randn(n, generator=gen).to(cuda).requires_grad_(True) for _ in range(2))
+        o0, o1 = ops.split_rows_linear(x, n0, w0, b0, w1, b1, precision="fp32")
+        g0, g1 = torch.randn(n0, n, generator=gen).to(cuda), torch.randn(m - n0, n, generator=gen).to(cuda)
+        ((o0 * g0).sum() + (o1 * g1).sum()).backward()
+        ref = [t.detach().double().requires_grad_(True) for t in (x, w0, b0, w1, b1)]
+        r0 = torch.nn.functional.linear(ref[0][:n0], ref[1], ref[2])
+        r1 = torch.nn.functional.linear(ref[0][n0:], ref[3], ref[4])
+        ((r0 * g0.double()).sum() + (r1 * g1.double()).sum()).backward()
+        tol = lambda t: dict(rtol=1e-4, atol=1e-5 * max(1.0, float(t.abs().max()) if t.numel() else 1.0))
+        torch.testing.assert_close(o0.double(), r0.detach(), **tol(r0))
+        torch.testing.assert_close(o1.double(), r1.detach(), **tol(r1))
+        for got, want in zip((x, w0, b0, w1, b1), ref):
+            want_g = want.grad if want.grad is not None else torch.zeros_like(want)
+            torch.testing.assert_close(got.grad.double(), want_g, **tol(want_g))
+
+
+def test_keep_bits_prefetch_is_bit_identical(cuda):
+    """Drawing the GCL dropout keep-bits of a stack ahead on the side stream (ops.prefetch_keep_bits) uses the same seeds in
+    the same order as drawing them inside each layer call: outputs and every gradient are bit-identical."""
+    import itertools
+    import polyphemus_b200 as pb
+    from polyphemus_b200 import ops
+
+    g, _ = _graph(cuda, bsz=6, n_bars=4, p=0.3, seed=21)
+    pb.set_precision("bf16")
+    try:
+        results = []
+        for prefetch in (True, False):
+            torch.manual_seed(5)
+            gcn = pb.GCN(input_dim=256, hidden_dim=256, n_layers=3, num_relations=6, batch_norm=True, dropout=0.0).to(cuda).train()
+            for layer in gcn.layers:
+                layer.dropout = 0.1
+            ops._bits_prefetch = prefetch
+            ops._seed_counter = itertools.count()
+            g.x = torch.randn(g.num_nodes, 256, generator=torch.Generator().manual_seed(1)).to(cuda).requires_grad_(True)
+            y = gcn(g)
+            y.square().sum().backward()
+            results.append([y.detach().clone(), g.x.grad.clone()] + [p.grad.clone() for p in gcn.parameters()])
+        for a, b in zip(*results):
+            assert torch.equal(a, b)
+    finally:
+        ops._bits_prefetch = True
+        pb.set_precision("fp32")
+
+
 # ------------------------------------------------------------------------------------------------- BatchNorm
 @pytest.mark.parametrize("m,d", [(37, 64), (4000, 512), (70001, 256)])
 def test_bn_relu_res_fwd_bwd(cuda, m, d):

@@ -183,7 +183,8 @@ def _vae_batch(ref, cuda):
     return device_batch(host, cuda, onehot=True)
 
 
-@pytest.mark.parametrize("content", ["token_ids", "onehot", "token_ids_lazy_logits", "token_ids_lazy_unfolded"])
+@pytest.mark.parametrize("content", ["token_ids", "onehot", "token_ids_lazy_logits", "token_ids_lazy_logits_onematrix",
+                                     "token_ids_lazy_unfolded"])
 def test_vae_training_step_matches_reference_golden(cuda, content):
     """Whole drop-in surface: VAE(graph) -> ((s_logits, c_logits), mu, log_var), reference loss, all gradients,
     BatchNorm running statistics; inputs go through the device graph builder (one empty bar included).
@@ -202,6 +203,8 @@ def test_vae_training_step_matches_reference_golden(cuda, content):
             graph.c_tokens = None
         if content.startswith("token_ids_lazy"):     # what train.TrainStep does: loss straight from the head outputs
             vae.decoder.c_decoder.materialize_logits = False
+        if content == "token_ids_lazy_logits_onematrix":   # PB200_SPLIT_HEADS=0: one [drum | non-drum | duration] matrix for all rows
+            pb.ops._split_heads = False
         if content == "token_ids_lazy_unfolded":
             # an active dropout between chord_decoder and the heads forbids composing them; p = 1e-12 keeps every
             # element and scales by exactly 1.0f, so the separate-heads path must reproduce the same golden numbers
@@ -210,7 +213,8 @@ def test_vae_training_step_matches_reference_golden(cuda, content):
         c_parts = c_logits
         if content.startswith("token_ids_lazy"):
             assert isinstance(c_logits, pb.vae.LogitParts)
-            assert (c_parts.combined is not None or c_parts.split is not None) == (content == "token_ids_lazy_logits")
+            assert (c_parts.split is not None) == (content == "token_ids_lazy_logits")
+            assert (c_parts.combined is not None) == (content == "token_ids_lazy_logits_onematrix")
             c_logits = c_parts.dense()
         # mu / log_var sit behind a BatchNorm over a batch of 4 sequences: reference self-noise level
         torch.testing.assert_close(mu.detach().cpu(), torch.from_numpy(ref["mu"]), rtol=1e-4, atol=2e-5)
@@ -240,6 +244,7 @@ def test_vae_training_step_matches_reference_golden(cuda, content):
                                            atol=1e-5, msg=k)
     finally:
         pb.set_precision("fp32")
+        pb.ops._split_heads = True
 
 
 def test_vae_bf16_mode_tracks_fp32(cuda):
