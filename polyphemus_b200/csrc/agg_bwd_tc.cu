@@ -401,6 +401,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) agg_bwd_tc_kernel(
 // still has a source to process (then the copies are simply issued after it) and a blocking wait otherwise — a
 // blocked warp only ever waits for positions older than everything it still has to consume, so the oldest unconsumed
 // edge can always proceed. Sources with more than 32 out-edges are processed in chunks of 32 (copy, wait, consume).
+// The parity of `empty` is only trusted once the shared counter `mma_front` says the stage's previous use has been
+// issued (a warp can be more than a lap of the ring ahead of the tensor core when out-degrees are skewed).
 #ifndef PB_RG_WARPS
 #define PB_RG_WARPS 15
 #endif
