@@ -448,6 +448,15 @@ def test_agg_bwd_tensor_core_foreign_graph_high_degree(cuda, act, d):
     assert torch.equal(gx1, gx2) and torch.equal(parts1, parts2) and torch.equal(gw1, gw2)
     scale = float(gw0.abs().max())
     torch.testing.assert_close(gw1, gw0, rtol=1e-4, atol=2e-5 * scale)
+    if act == "bf16":
+        # forward on the same graph (in-degree > 32 on node 3): the pipelined kernel (d = 512, bf16 rows) and the generic one
+        # (same values as fp32 rows) compute the same operand up to the rounding of the dropout scaling and the bf16 store
+        a_b = torch.full((n, k), float("nan"), dtype=torch.bfloat16, device=cuda)
+        a_f = torch.full((n, k), float("nan"), dtype=torch.bfloat16, device=cuda)
+        ffi.check(lib.pb_agg_fwd(plan.ref(), ptr(x), d, ptr(table), ptr(a_b), None, k, ffi.PB_BF16, ptr(bits), p_drop, ffi.PB_BF16, st()), "agg_fwd")
+        x32 = x.float()
+        ffi.check(lib.pb_agg_fwd(plan.ref(), ptr(x32), d, ptr(table), ptr(a_f), None, k, ffi.PB_BF16, ptr(bits), p_drop, ffi.PB_F32, st()), "agg_fwd")
+        torch.testing.assert_close(a_b.float(), a_f.float(), rtol=1.6e-2, atol=1e-3)
 
 
 def test_split_rows_linear_matches_two_linears(cuda):
