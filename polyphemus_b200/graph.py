@@ -24,7 +24,9 @@ class CsrPlan:
     """Destination-/source-sorted views of an edge list (pb_csr_build); shared by all layers of a GCN."""
 
     def __init__(self, edge_index: torch.Tensor, edge_type: torch.Tensor, edge_dist: torch.Tensor,
-                 num_nodes: int, n_relations: int = _ffi.N_RELATIONS):
+                 num_nodes: int, n_relations: int = _ffi.N_RELATIONS, node_order: Optional[torch.Tensor] = None):
+        """``node_order`` (int32 permutation of the rows): visiting order of the kernels, see ``set_node_order``; given here
+        the visit metadata and the backward's record stream are built once instead of once per order."""
         _ffi.require_cuda(edge_index, edge_type, edge_dist)
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise ValueError("edge_index must be int64 [2, E]")
@@ -59,6 +61,10 @@ class CsrPlan:
                                      self.dist_perm.data_ptr(), self.dist_items.data_ptr(),
                                      self.dist_item_ptr.data_ptr(), None, None, None, None)
         self.node_order = None
+        if node_order is not None:
+            assert node_order.dtype == torch.int32 and node_order.numel() == n
+            self.node_order = node_order.contiguous()
+            self.struct.node_order = self.node_order.data_ptr()
         self.visit_meta = torch.empty((n, 4), dtype=torch.int32, device=dev)
         self._build_visit_meta()
 
@@ -116,12 +122,13 @@ class StructuredPlan:
         pos_sorted = torch.arange(n, device=dev) + shift.index_select(0, group.index_select(0, order).long())
         self.pos = torch.empty(n, dtype=torch.int64, device=dev).index_copy_(0, order, pos_sorted)  # node -> padded row
         slot = (graph.edge_type.to(torch.int16) - 3).clamp_(min=0).to(torch.uint8)   # track rels -> 0, onset 1, next 2
-        self.plan = CsrPlan(self.pos[graph.edge_index], slot, graph.edge_dist, self.n_padded, n_relations=3)
         # visit the rows bar by bar (original node order), the padding rows last: a bar's rows live in four distant
         # group regions, touching them together keeps every gathered row in L2 until its last use
         is_pad = torch.ones(self.n_padded, dtype=torch.bool, device=dev).index_fill_(0, self.pos, False)
         pads = torch.arange(self.n_padded, device=dev)[is_pad] if self.n_padded > n else self.pos[:0]
-        self.plan.set_node_order(torch.cat((self.pos, pads)).to(torch.int32))
+        order = torch.cat((self.pos, pads)).to(torch.int32)
+        self.plan = CsrPlan(self.pos[graph.edge_index], slot, graph.edge_dist, self.n_padded, n_relations=3,
+                            node_order=order)
         self.groups = _ffi.GroupsStruct(4, 0, (ctypes.c_int64 * 4)(*starts), (ctypes.c_int64 * 4)(*counts))
 
     def groups_ref(self):
